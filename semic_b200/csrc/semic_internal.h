@@ -1,0 +1,113 @@
+// semic_internal.h -- types shared between the C-ABI translation unit and the two kernel
+// translation units (fast / strict arithmetic).  Not part of the public boundary.
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "semic_b200.h"
+
+namespace semic {
+
+// albedo scheme ids (string compares of surface_physics.f90:340-360 resolved once on the host)
+enum { SCHEME_NONE = 0, SCHEME_SLATER = 1, SCHEME_DENBY = 2, SCHEME_ISBA = 3, SCHEME_ALEX = 4, SCHEME_UNKNOWN = 5,
+       SCHEME_RUNTIME = 6 /* template value: switch on DevPar::scheme at run time */ };
+
+// Tile geometry of the persistent kernel: 8 consumer warps + 1 producer (TMA) warp per CTA.
+constexpr int kConsumerWarps = 8;
+constexpr int kConsumers     = kConsumerWarps * 32;      // 256
+constexpr int kThreads       = kConsumers + 32;          // 288
+constexpr int kStages        = 4;                        // days of forcing in flight per CTA
+constexpr int kLdAlign       = 1024;                     // leading dimensions are multiples of this (>= max tile)
+constexpr int kForcingRows   = 9;
+constexpr int kExtRows       = 5;                        // tsurf alb smb melt acc overrides
+
+// Parameters in the form the kernels use.  Everything here is either a member of
+// surface_param_class or a PARAMETER-ONLY expression evaluated once on the host with the
+// reference's own operation order (so hoisting it changes no bits).
+struct DevPar {
+    double ceff, albi, albl, alb_smax, alb_smin, hcrit, rcrit, amp, csh, clh, tmin, tmax,
+           tstic, tsticsub, tau_a, tau_f, w_crit, mcrit, afac, tmid;
+    // exact hoists (same operations on the same operands as the reference performs per point)
+    double csh_cap;          // csh*cap                      (:387 prefix)
+    double rhow_clm;         // rhow*clm                     (:266,:286)
+    double one_m_frz;        // 1.0 - f_rz, f_rz = rcrit     (:284,:298)
+    double hcrit_eps;        // hcrit + epsil                (:338)
+    double slater_f;         // 1.0/(t0 - tmin)              (:518)
+    double smax_m_smin;      // alb_smax - alb_smin          (:487,:529,:541,:361)
+    double isba_dry;         // tau_a*tstic/tau, tau = tstic (:484)
+    double isba_wet;         // dexp(-tau_f*tstic/tau)       (:486)  host libm, like the reference
+    double isba_wcr;         // w_crn/rhow                   (:487)
+    // tolerance-funded reciprocals (fast arithmetic only; <= 1 ulp each)
+    double sub_over_ceff;    // tsticsub/ceff
+    double ceff_over_sub;    // ceff/tsticsub
+    double tstic_over_ceff;  // tstic/ceff
+    double ceff_over_tstic;  // ceff/tstic
+    double inv_tstic;        // 1/tstic
+    double inv_rhow_clm;     // 1/(rhow*clm)
+    double inv_hcrit_eps;    // 1/(hcrit+epsil)
+    double inv_amp;          // 1/amp
+    double inv_mcrit;        // 1/mcrit
+    double isba_new;         // tstic/(w_crn/rhow)*(alb_smax-alb_smin)
+    double frz_rhow_clm;     // (1-f_rz)*rhow*clm
+    int    n_ksub;
+    int    scheme;
+};
+
+struct RunArgs {
+    // state slab (device): field f of point i at slab[f*ld + i]
+    double       *slab;
+    const int    *mask;
+    int           nx;
+    int           ld;
+    // forcing: element (day d, var v, point i) at forcing[((day0+d) % nwin)*f_day_stride + f_var_off[v] + i]
+    const double *forcing;
+    long long     f_day_stride;
+    long long     f_var_off[kForcingRows];
+    int           f_nwin;
+    int           f_day0;
+    // external override fields (validation layout, 8 rows per day) or NULL
+    const double *vali;
+    long long     v_day_stride;
+    long long     v_var_stride;
+    // daily output ring or NULL: row ((d - out_start) % o_nring), var v, point i
+    double       *out;
+    long long     o_day_stride;
+    long long     o_var_stride;
+    int           o_nring;
+    int           o_nvar;       // 8, or 9 with the branch bitmap
+    int           out_start;    // first day (0-based within this run) that is written
+    int           ndays;
+    int           eb_steps;     // sub-steps of energy_balance per day (n_ksub; 1 for energy_balance alone; 0 = skip)
+    int           do_mb;        // run mass_balance
+    int           write_forcing_back;   // store the last day's forcing into the slab (multi-day runs)
+    DevPar        P;
+    semic_bnd     B;
+};
+
+// ensemble (config 5): every particle starts from the same initial slab
+struct EnsArgs {
+    const double *slab0;        // initial state [31][ld]
+    const int    *mask;
+    int           nx, ld;
+    const double *forcing;      // [ntime][9][ldf]
+    const double *vali;         // [ntime][8][ldf]
+    long long     f_day_stride, f_var_stride, v_day_stride, v_var_stride;
+    const double *inv_var;      // [4][ld]  1/var of vali stt, melt, smb, swnet (zero variance -> inf, like utils.f90:36)
+    const DevPar *pars;         // [npar]
+    int           npar;
+    int           ntime, nloop;
+    double       *partial;      // [npar][ntiles] per-CTA partial sums (deterministic two-stage reduce)
+    int           ntiles;       // ceil(nx/32)
+};
+
+// implemented once per arithmetic mode (semic_kernels_fast.cu / semic_kernels_strict.cu)
+cudaError_t launch_run_fast(const RunArgs &a, bool generic, int ppt, cudaStream_t st, int *launches);
+cudaError_t launch_run_strict(const RunArgs &a, bool generic, int ppt, cudaStream_t st, int *launches);
+// inv_var and partial are scratch buffers owned by the caller; sumsq_dev receives npar doubles
+cudaError_t launch_vali_invvar(const EnsArgs &a, double *inv_var, cudaStream_t st);
+cudaError_t launch_ensemble_fast(const EnsArgs &a, double *sumsq_dev, cudaStream_t st);
+cudaError_t launch_elementals_fast(int which, const double *const *in, const int *mask, const double *sc,
+                                   double *const *out, int n, cudaStream_t st);
+
+}  // namespace semic

@@ -1,0 +1,858 @@
+// semic_kernels.cuh -- the SEMIC point-day physics and the persistent multi-day kernel (sm_100a).
+//
+// Included twice: SEMIC_STRICT=0 (semic_kernels_fast.cu, FMA contraction on, reciprocal
+// multiplies, custom exp) and SEMIC_STRICT=1 (semic_kernels_strict.cu, compiled with
+// -fmad=false: the reference's operation order, IEEE division, no contraction; only the libm
+// calls exp/acos/pow/tanh differ from a gfortran build, by the 1-2 ulp of libdevice vs glibc).
+//
+// What it replaces: surface_energy_and_mass_balance (surface_physics.f90:138-153), i.e.
+// n_ksub x energy_balance (:158-214) + mass_balance (:232-374) with the elementals (:378-560),
+// fused per grid point so that every point-day costs 9 forcing loads and (optionally) 8 output
+// stores instead of ~47 array sweeps per sub-step.
+//
+// Kernel shape (k_run): persistent CTAs, one per SM slot.  A CTA owns tiles of T = 256*PPT
+// consecutive points and walks each tile through ALL days with the prognostic state
+// (tsurf, hsnow, hice, alb, alb_snow, qmr_res) in registers.  Warp 8 is the producer: one lane
+// issues 1-D TMA bulk copies (cp.async.bulk, SASS UBLKCP) of the 9 forcing rows of the next
+// days into a kStages-deep shared-memory ring guarded by full/empty mbarriers; warps 0-7
+// consume a stage with conflict-free LDS (values are read where first needed), release it, and store the daily
+// diagnostics coalesced.  No tensor cores: nothing here is a contraction.
+#pragma once
+
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdint.h>
+
+#include "semic_internal.h"
+
+#ifndef SEMIC_STRICT
+#error "define SEMIC_STRICT to 0 or 1 before including semic_kernels.cuh"
+#endif
+
+namespace semic {
+namespace SEMIC_MODE_NS {
+
+#define DEVI __device__ __forceinline__
+
+// constants, surface_physics.f90:14-25
+constexpr double c_pi    = 3.141592653589793238462643;
+constexpr double c_t0    = 273.15;
+constexpr double c_sigm  = 5.67e-8;
+constexpr double c_eps   = 0.62197;
+constexpr double c_cls   = 2.83e6;
+constexpr double c_clv   = 2.5e6;
+constexpr double c_rhow  = 1000.0;
+constexpr double c_hsmax = 5.0;
+
+// ------------------------------------------------------------------------------------------------
+// arithmetic helpers
+// ------------------------------------------------------------------------------------------------
+// Literal doubles of the hot loop live in the constant bank so that they are direct c[3][..]
+// operands of DFMA/DMUL; as immediates ptxas re-materialises each one with two UMOVs per use.
+__device__ __constant__ double kc[24] = {
+    6755399441055744.0,           //  0  1.5*2^52
+    1.4426950408889634,           //  1  log2(e)
+    -6.93147180369123816490e-01,  //  2  -ln2 hi
+    -1.90821492927058770002e-10,  //  3  -ln2 lo
+    2.5022322536502990e-08,       //  4  exp polynomial, degree 11 .. 2
+    2.7630903488173108e-07,       //  5
+    2.7557514545882439e-06,       //  6
+    2.4801491039099165e-05,       //  7
+    1.9841269589115497e-04,       //  8
+    1.3888888945916380e-03,       //  9
+    8.3333333334550432e-03,       // 10
+    4.1666666666519754e-02,       // 11
+    1.6666666666666477e-01,       // 12
+    5.0000000000000122e-01,       // 13
+    273.15,                       // 14  t0
+    611.2 * 0.62197,              // 15  611.2*eps
+    611.2 * (0.62197 - 1.0),      // 16  611.2*(eps-1)
+    5.67e-8,                      // 17  sigm
+    22.46, 272.62,                // 18 19  ei_sat a, b
+    17.62, 243.12,                // 20 21  ew_sat a, b
+    2.83e6, 2.5e6                 // 22 23  cls, clv
+};
+#if SEMIC_STRICT
+DEVI double fdiv(double n, double d) { return n / d; }    // CUDA double division is IEEE round-to-nearest
+DEVI double fexp(double x) { return exp(x); }
+#else
+// reciprocal from the MUFU.RCP64H seed + two Newton steps (operands here are normal, far from
+// 0/inf: temperatures, pressures, positive parameters).  ~1 ulp.
+DEVI double frcp(double d)
+{
+    double r;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(d));
+    double e = fma(-d, r, 1.0);
+    r = fma(r, e, r);
+    e = fma(-d, r, 1.0);
+    r = fma(r, e, r);
+    return r;
+}
+DEVI double fdiv(double n, double d) { return n * frcp(d); }
+// exp for |x| < 700 without special-case handling: Cody-Waite reduction by ln2 and the
+// degree-11 minimax polynomial (max rel. error 4e-18 before rounding).
+DEVI double fexp(double x)
+{
+    const double magic = kc[0];                           // 1.5 * 2^52
+    double t = fma(x, kc[1], magic);
+    const int k = __double2loint(t);
+    const double kf = t - magic;
+    double r = fma(kf, kc[2], x);
+    r = fma(kf, kc[3], r);
+    double p = kc[4];
+    p = fma(p, r, kc[5]);
+    p = fma(p, r, kc[6]);
+    p = fma(p, r, kc[7]);
+    p = fma(p, r, kc[8]);
+    p = fma(p, r, kc[9]);
+    p = fma(p, r, kc[10]);
+    p = fma(p, r, kc[11]);
+    p = fma(p, r, kc[12]);
+    p = fma(p, r, kc[13]);
+    p = fma(p, r, 1.0);
+    p = fma(p, r, 1.0);
+    return __hiloint2double(__double2hiint(p) + (k << 20), __double2loint(p));
+}
+#endif
+
+// ------------------------------------------------------------------------------------------------
+// elementals (also exported one by one through the C-ABI for the known-answer tests)
+// ------------------------------------------------------------------------------------------------
+
+// sensible_heat_flux, surface_physics.f90:378-389
+DEVI double sensible_heat_flux(double ts, double ta, double wind, double rhoa, double csh, double cap)
+{
+    return (((csh * cap) * rhoa) * wind) * (ts - ta);
+}
+
+// ei_sat / ew_sat, surface_physics.f90:546-560, selected by ts < t0 as latent_heat_flux does (:415)
+DEVI double esat(double ts, bool ice)
+{
+#if SEMIC_STRICT
+    const double a = ice ? 22.46 : 17.62;
+    const double b = ice ? 272.62 : 243.12;
+    return 611.2 * fexp(fdiv(a * (ts - c_t0), (b + ts) - c_t0));
+#else
+    const double a = ice ? kc[18] : kc[20];
+    const double b = ice ? kc[19] : kc[21];
+    const double x = ts - kc[14];
+    return 611.2 * fexp((a * x) * frcp(b + x));
+#endif
+}
+
+// latent_heat_flux, surface_physics.f90:393-430; returns q = subl (ice) or evap (water) in kg/(s m2)
+DEVI double latent_q(double ts, double wind_clh_rho, double shum, double sp, bool ice)
+{
+#if SEMIC_STRICT
+    const double es = esat(ts, ice);
+    const double shum_sat = fdiv(es * c_eps, (es * (c_eps - 1.0)) + sp);
+#else
+    // 611.2 folded into the two eps factors: es*eps/(es*(eps-1)+sp)
+    const double a = ice ? kc[18] : kc[20];
+    const double b = ice ? kc[19] : kc[21];
+    const double x = ts - kc[14];
+    const double e = fexp((a * x) * frcp(b + x));
+    const double shum_sat = (e * kc[15]) * frcp(fma(e, kc[16], sp));
+#endif
+    return wind_clh_rho * (shum_sat - shum);
+}
+
+// longwave_upward, surface_physics.f90:434-438
+DEVI double longwave_upward(double ts, double sigma)
+{
+#if SEMIC_STRICT
+    return (((sigma * ts) * ts) * ts) * ts;
+#else
+    const double t2 = ts * ts;
+    return sigma * (t2 * t2);
+#endif
+}
+
+// diurnal_cycle, surface_physics.f90:444-472.  Returns the branch id (0 below only, 1 interior, 2 above only).
+DEVI int diurnal_cycle(double amp, double tmean, double &above, double &below)
+{
+    if (tmean + amp < 0.0) {                        // :459
+        below = tmean;
+        above = 0.0;
+        return 0;
+    }
+    above = tmean;
+    below = 0.0;
+    if (fabs(tmean) < amp) {                        // :465
+        // Reference operation order and IEEE division in BOTH arithmetic modes: for tmean -> -amp the
+        // numerator of `above` cancels to O(eps^1.5), so only the reference's own rounding sequence
+        // reproduces its digits.  The branch runs on the minority of days with a freeze/thaw cycle.
+        const double r = __ddiv_rn(tmean, amp);
+        double tmp1 = 0.0, tmp2 = 0.0;              // :452-453
+        if (fabs(r) < 1.0) {                        // :454 (can differ from :465 only by the rounding of the quotient)
+            tmp1 = acos(r);                         // :455
+            tmp2 = sqrt(__dsub_rn(1.0, __ddiv_rn(__dmul_rn(tmean, tmean), __dmul_rn(amp, amp))));      // :456
+        }
+        const double at2 = __dmul_rn(amp, tmp2);
+        above = __ddiv_rn(__dadd_rn(__dadd_rn(__dmul_rn(-tmean, tmp1), at2), __dmul_rn(c_pi, tmean)),
+                          __dsub_rn(c_pi, tmp1));                                                      // :467
+        below = __ddiv_rn(__dsub_rn(__dmul_rn(tmean, tmp1), at2), tmp1);                               // :469
+        return 1;
+    }
+    return 2;
+}
+
+// albedo_slater, surface_physics.f90:503-530
+DEVI double albedo_slater(double tsurf, const DevPar &P)
+{
+    double tm = 0.0;
+    if (tsurf >= P.tmin && tsurf <= P.tmax) tm = P.slater_f * (tsurf - P.tmin);
+    if (tsurf > c_t0) tm = 1.0;
+#if SEMIC_STRICT
+    return P.alb_smax - (P.smax_m_smin * pow(tm, 3.0));
+#else
+    return fma(-P.smax_m_smin, tm * tm * tm, P.alb_smax);
+#endif
+}
+
+// albedo_denby, surface_physics.f90:535-542
+DEVI double albedo_denby(double melt, const DevPar &P)
+{
+#if SEMIC_STRICT
+    return P.alb_smin + (P.smax_m_smin * fexp(fdiv(-melt, P.mcrit)));
+#else
+    return fma(P.smax_m_smin, fexp(-melt * P.inv_mcrit), P.alb_smin);
+#endif
+}
+
+// albedo_isba, surface_physics.f90:476-496 (called with tau = tstic, :345)
+DEVI double albedo_isba(double alb, double sf, double melt, const DevPar &P)
+{
+    const double alb_dry = alb - P.isba_dry;
+    const double alb_wet = ((alb - P.alb_smin) * P.isba_wet) + P.alb_smin;
+#if SEMIC_STRICT
+    const double alb_new = fdiv(sf * P.tstic, P.isba_wcr) * P.smax_m_smin;
+    double w_alb = 0.0;
+    if (melt > 0.0) w_alb = 1.0 - fdiv(melt, P.mcrit);
+#else
+    const double alb_new = sf * P.isba_new;
+    double w_alb = 0.0;
+    if (melt > 0.0) w_alb = fma(-melt, P.inv_mcrit, 1.0);
+#endif
+    w_alb = fmin(1.0, fmax(w_alb, 0.0));
+    double a = (((1.0 - w_alb) * alb_dry) + (w_alb * alb_wet)) + alb_new;
+    return fmin(P.alb_smax, fmax(a, P.alb_smin));
+}
+
+// ------------------------------------------------------------------------------------------------
+// one point, one day
+// ------------------------------------------------------------------------------------------------
+struct Pt {
+    // carried day to day (surface_physics.f90:56-90)
+    double tsurf, hsnow, hice, alb, alb_snow, qmr_res;
+    // diagnostics of the current day (also carried when a boundary flag freezes them)
+    double t2m, melt, melted_snow, melted_ice, refr, smb, acc, lhf, shf, lwu, subl, evap,
+           smb_snow, smb_ice, runoff, qmr, amp;
+    int mask;
+};
+
+#define BND(x) (GENERIC && (B.x != 0))
+
+// `row` points at this point's column of the day's forcing (a shared-memory stage in k_run, global
+// memory in k_ensemble): variable v is row[v*T].  Values are read where they are first needed (LDS
+// is cheap, registers across the sub-step loop are not); `swd_out` returns the day's shortwave for
+// the swnet diagnostic.
+template <int SCHEME, bool GENERIC>
+DEVI unsigned point_day(Pt &s, const double *row, const long long T, const DevPar &P, const semic_bnd &B,
+                        const int eb_steps, const int do_mb, double &swd_out)
+{
+    unsigned branch = 0;
+    const int mask = s.mask;
+    const bool gate = (mask == 2) || (s.hsnow > 0.0);                 // :201,:209 (hsnow is constant over the sub-steps)
+    if (gate) branch |= SEMIC_B_GATE;
+
+    double ts = s.tsurf;
+    double t2m = row[SEMIC_V_T2M * T];
+    double shf = s.shf, lhf = s.lhf, subl = s.subl, evap = s.evap, lwu = s.lwu, qmr = s.qmr;
+
+    // ---------------- energy_balance x eb_steps (:149-151, :158-214) ----------------
+    {
+        const double wind = row[SEMIC_V_WIND * T], rhoa = row[SEMIC_V_RHOA * T];
+        const double swd = row[SEMIC_V_SWD * T];
+        swd_out = swd;
+        // exact hoists: literal left-to-right prefixes of :387, :420/:427 and :194
+        const double shf_c  = (P.csh_cap * rhoa) * wind;
+        const double lhf_c  = (P.clh * wind) * rhoa;
+        const double rad    = ((1.0 - s.alb) * swd) + row[SEMIC_V_LWD * T];
+        const double qq = row[SEMIC_V_QQ * T], sp = row[SEMIC_V_SP * T];
+        const double qmr_res = s.qmr_res;
+        double q_last = 0.0, over = 0.0;
+        bool ice_last = false, any = false;
+        const int nsub = GENERIC ? eb_steps : P.n_ksub;
+        for (int k = 0; k < nsub; ++k) {
+            any = true;
+            if (!BND(shf)) shf = shf_c * (ts - t2m);                               // :173
+            if (!BND(lhf)) {                                                       // :179-185
+#if SEMIC_STRICT
+                const bool ice = ts < c_t0;                                        // :415
+                const double q = latent_q(ts, lhf_c, qq, sp, ice);
+                lhf = q * (ice ? c_cls : c_clv);                                   // :421,:428
+#else
+                const bool ice = ts < kc[14];
+                const double q = latent_q(ts, lhf_c, qq, sp, ice);
+                lhf = q * (ice ? kc[22] : kc[23]);
+#endif
+                q_last = q;
+                ice_last = ice;
+                if (GENERIC) { subl = ice ? q : 0.0; evap = ice ? 0.0 : q; }
+            }
+            if (GENERIC) subl = fdiv(subl, c_rhow);                                // :186 (every sub-step, Q3)
+#if SEMIC_STRICT
+            lwu = longwave_upward(ts, c_sigm);                                     // :191
+#else
+            lwu = longwave_upward(ts, kc[17]);
+#endif
+            const double qsb = (((rad - lwu) - shf) - lhf) - qmr_res;              // :194
+            over = 0.0;                                                            // :197
+            if (!BND(tsurf)) {                                                     // :198
+#if SEMIC_STRICT
+                ts = ts + fdiv(qsb * P.tsticsub, P.ceff);                          // :199
+                if (gate && ts > c_t0) {                                           // :201-204
+                    over = ts - c_t0;
+                    ts = c_t0;
+                }
+#else
+                ts = fma(qsb, P.sub_over_ceff, ts);
+                if (gate && ts > kc[14]) {
+                    over = ts - kc[14];
+                    ts = kc[14];
+                }
+#endif
+            }
+            if (gate) {                                                            // :209-211 (Q1: forcing t2m is mutated)
+#if SEMIC_STRICT
+                t2m = t2m + fdiv((shf + lhf) * P.tsticsub, P.ceff);
+#else
+                t2m = fma(shf + lhf, P.sub_over_ceff, t2m);
+#endif
+            }
+        }
+        if (any) {
+            // only the last sub-step's qmr survives (:197, Q2)
+#if SEMIC_STRICT
+            qmr = fdiv(over * P.ceff, P.tsticsub);                                 // :202 (0 when the clamp did not fire)
+#else
+            qmr = over * P.ceff_over_sub;
+#endif
+            if (over > 0.0) branch |= SEMIC_B_CLAMP;
+            if (!BND(lhf)) {
+                if (ice_last) branch |= SEMIC_B_TS_LT_T0;
+                if (!GENERIC) {                                                    // :410-411,:420,:427 then :186
+#if SEMIC_STRICT
+                    subl = ice_last ? fdiv(q_last, c_rhow) : 0.0;
+#else
+                    subl = ice_last ? q_last * 1.0e-3 : 0.0;
+#endif
+                    evap = ice_last ? 0.0 : q_last;
+                }
+            }
+        }
+    }
+
+    double hsnow = s.hsnow, hice = s.hice, alb = s.alb, alb_snow = s.alb_snow, qmr_res = s.qmr_res;
+    double melt = s.melt, melted_snow = s.melted_snow, melted_ice = s.melted_ice, refr = s.refr;
+    double smb = s.smb, acc = s.acc, smb_snow = s.smb_snow, smb_ice = s.smb_ice, runoff = s.runoff, amp = s.amp;
+
+    // ---------------- mass_balance (:232-374) ----------------
+    if (!GENERIC || do_mb) {
+        const double sf = row[SEMIC_V_SF * T], rf = row[SEMIC_V_RF * T];
+        if (!BND(amp)) amp = P.amp;                                                // :246-248
+#if SEMIC_STRICT
+        const double tmean = (ts - c_t0) + (fdiv(qmr, P.ceff) * P.tstic);          // :249
+#else
+        const double tmean = fma(qmr, P.tstic_over_ceff, ts - kc[14]);
+#endif
+        double above, below;
+        const int dbr = diurnal_cycle(amp, tmean, above, below);
+        branch |= (dbr == 1 ? SEMIC_B_DIURNAL_LO : (dbr == 2 ? SEMIC_B_DIURNAL_HI : 0));
+        qmr = 0.0;                                                                 // :250
+
+        double qmelt = 0.0, qcold = 0.0;
+        if (mask >= 1) {                                                           // :252-261
+#if SEMIC_STRICT
+            qmelt = fmax(0.0, fdiv(above * P.ceff, P.tstic));
+            qcold = fmax(0.0, fdiv(fabs(below) * P.ceff, P.tstic));
+#else
+            qmelt = fmax(0.0, above * P.ceff_over_tstic);
+            qcold = fmax(0.0, fabs(below) * P.ceff_over_tstic);
+#endif
+        }
+#if SEMIC_STRICT
+        if (!BND(melt)) melt = fdiv(qmelt, P.rhow_clm);                            // :266
+        const double hs_rate = fdiv(hsnow, P.tstic);
+#else
+        if (!BND(melt)) melt = qmelt * P.inv_rhow_clm;
+        // IEEE quotient: when all snow melts, hsnow - (hsnow/tstic)*tstic decides between "bare" and a
+        // one-ulp ghost snow layer (which keeps the :201 gate on over land); keep the reference's rounding
+        const double hs_rate = __ddiv_rn(hsnow, P.tstic);
+#endif
+        melted_snow = fmin(melt, hs_rate);                                         // :269
+        melted_ice  = melt - melted_snow;                                          // :270
+        if (!BND(melt)) {                                                          // :272-280
+            if (mask == 2) {
+                melt = melted_snow + melted_ice;
+            } else {
+                melt = melted_snow;
+                melted_ice = 0.0;
+            }
+        }
+
+        double refrozen_rain = 0.0, refrozen_snow = 0.0;                           // Q5: defined as 0 under bnd%refr
+        if (!BND(refr)) {                                                          // :283-299
+#if SEMIC_STRICT
+            refr = fdiv(qcold, P.rhow_clm);                                        // :286
+#else
+            refr = qcold * P.inv_rhow_clm;
+#endif
+            refrozen_rain = fmin(refr, rf);                                        // :287
+            refrozen_snow = fmax(refr - refrozen_rain, 0.0);                       // :289
+            refrozen_snow = fmin(refrozen_snow, melted_snow);                      // :291
+            refrozen_rain = P.rcrit * fmin(hs_rate, refrozen_rain);                // :293
+            refrozen_snow = P.rcrit * fmin(hs_rate, refrozen_snow);                // :294
+            refr = refrozen_rain + refrozen_snow;                                  // :295
+#if SEMIC_STRICT
+            qmr = qmr - (((P.one_m_frz * refr) * c_rhow) * 3.30e5);                // :298
+#else
+            qmr = -(refr * P.frz_rhow_clm);
+#endif
+        }
+
+        runoff = (melt + rf) - refrozen_rain;                                      // :302-303
+        if (!BND(acc)) acc = (sf - subl) + refr;                                   // :307
+        if (!BND(smb)) smb_snow = ((sf - subl) - melted_snow) + refrozen_snow;     // :312
+
+        if (mask == 0) hsnow = 0.0;                                                // :315-320
+#if SEMIC_STRICT
+        else hsnow = fmax(0.0, hsnow + (smb_snow * P.tstic));
+#else
+        else hsnow = fmax(0.0, __dadd_rn(hsnow, __dmul_rn(smb_snow, P.tstic)));      // unfused, see hs_rate
+#endif
+        const double snow_to_ice = fmax(0.0, hsnow - c_hsmax);                     // :323
+        hsnow = hsnow - snow_to_ice;                                               // :324
+#if SEMIC_STRICT
+        const double s2i_rate = fdiv(snow_to_ice, P.tstic);
+        smb_ice = (s2i_rate - melted_ice) + refrozen_rain;                         // :325
+        hice = hice + (smb_ice * P.tstic);                                         // :326
+#else
+        const double s2i_rate = snow_to_ice * P.inv_tstic;
+        smb_ice = (s2i_rate - melted_ice) + refrozen_rain;
+        hice = fma(smb_ice, P.tstic, hice);
+#endif
+        if (!BND(smb)) {                                                           // :329-335
+            if (mask == 2) smb = (smb_snow + smb_ice) - s2i_rate;
+            else           smb = smb_snow + fmax(0.0, smb_ice - s2i_rate);
+        }
+        if (melt > 0.0) branch |= SEMIC_B_MELT_POS;
+        if (hsnow == 0.0) branch |= SEMIC_B_HSNOW_ZERO;
+        if (snow_to_ice > 0.0) branch |= SEMIC_B_SNOW2ICE;
+
+        if (!BND(alb)) {                                                           // :339 (Q6: the whole block is skipped)
+#if SEMIC_STRICT
+            const double f_alb = 1.0 - fexp(fdiv(-hsnow, P.hcrit_eps));            // :338
+#else
+            const double f_alb = 1.0 - fexp(-hsnow * P.inv_hcrit_eps);
+#endif
+            const int scheme = (SCHEME == SCHEME_RUNTIME) ? P.scheme : SCHEME;
+            if (scheme == SCHEME_SLATER)      alb_snow = albedo_slater(ts, P);     // :340-341
+            else if (scheme == SCHEME_DENBY)  alb_snow = albedo_denby(melt, P);    // :342-343
+            else if (scheme == SCHEME_ISBA)   alb_snow = albedo_isba(alb_snow, sf, melt, P);   // :344-346
+            else if (scheme == SCHEME_NONE)   alb_snow = P.alb_smax;               // :347-348
+            if (mask == 2)      alb = P.albi + (f_alb * (alb_snow - P.albi));      // :350-352
+            else if (mask == 1) alb = P.albl + (f_alb * (alb_snow - P.albl));      // :353-355
+            else if (mask == 0) alb = 0.06;                                        // :356-358
+            if (scheme == SCHEME_ALEX) {                                           // :360-363 (uses the mutated t2m)
+                alb_snow = P.alb_smin + (P.smax_m_smin * ((0.5 * tanh(P.afac * (t2m - P.tmid))) + 0.5));
+                alb = alb_snow;
+            }
+        }
+        qmr_res = (mask == 0) ? 0.0 : qmr;                                         // :368-372
+    }
+
+    s.tsurf = ts; s.hsnow = hsnow; s.hice = hice; s.alb = alb; s.alb_snow = alb_snow; s.qmr_res = qmr_res;
+    s.t2m = t2m; s.melt = melt; s.melted_snow = melted_snow; s.melted_ice = melted_ice; s.refr = refr;
+    s.smb = smb; s.acc = acc; s.lhf = lhf; s.shf = shf; s.lwu = lwu; s.subl = subl; s.evap = evap;
+    s.smb_snow = smb_snow; s.smb_ice = smb_ice; s.runoff = runoff; s.qmr = qmr; s.amp = amp;
+    return branch;
+}
+
+// ------------------------------------------------------------------------------------------------
+// mbarrier / TMA (1-D bulk copy) primitives, inline PTX
+// ------------------------------------------------------------------------------------------------
+DEVI uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+DEVI void mbar_init(uint64_t *bar, uint32_t count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+DEVI void mbar_fence_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+DEVI void mbar_expect_tx(uint64_t *bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+DEVI void mbar_arrive(uint64_t *bar)
+{
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+DEVI void mbar_wait(uint64_t *bar, uint32_t parity)
+{
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra DONE_%=;\n"
+        "bra WAIT_%=;\n"
+        "DONE_%=:\n"
+        "}\n" ::"r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+}
+// global -> shared bulk copy completing on an mbarrier (TMA unit, SASS UBLKCP); 16-byte aligned, size % 16 == 0
+DEVI void tma_load_1d(void *smem_dst, const void *gmem_src, uint32_t bytes, uint64_t *bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     smem_u32(smem_dst)),
+                 "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+
+// ------------------------------------------------------------------------------------------------
+// the persistent multi-day kernel
+// ------------------------------------------------------------------------------------------------
+template <bool GENERIC, int PPT>
+struct RunSmem {
+    static constexpr int T = kConsumers * PPT;
+    static constexpr int ROWS = kForcingRows + (GENERIC ? kExtRows : 0);
+    static constexpr int STAGES = (PPT == 1) ? kStages : 3;
+    static constexpr size_t stage_bytes = (size_t)ROWS * T * sizeof(double);
+    static constexpr size_t bytes = stage_bytes * STAGES + 2 * STAGES * sizeof(uint64_t);
+};
+
+// validation-layout rows that feed the overrides tsurf, alb, smb, melt, acc (example.f90:103-107)
+__device__ __constant__ int c_ext_var[kExtRows] = {SEMIC_O_STT, SEMIC_O_ALB, SEMIC_O_SMB, SEMIC_O_MELT, SEMIC_O_ACC};
+
+template <int SCHEME, bool GENERIC, int PPT, int MINB>
+__global__ void __launch_bounds__(kThreads, MINB) k_run(const __grid_constant__ RunArgs a)
+{
+    using SM = RunSmem<GENERIC, PPT>;
+    constexpr int T = SM::T;
+    constexpr int ROWS = SM::ROWS;
+    constexpr int NST = SM::STAGES;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    double *sbuf = reinterpret_cast<double *>(smem_raw);
+    uint64_t *full = reinterpret_cast<uint64_t *>(smem_raw + SM::stage_bytes * NST);
+    uint64_t *empty = full + NST;
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < NST; ++s) {
+            mbar_init(&full[s], 1);
+            mbar_init(&empty[s], kConsumerWarps);
+        }
+        mbar_fence_init();
+    }
+    __syncthreads();
+
+    const int ntiles = (a.nx + T - 1) / T;
+    bool ext_on[kExtRows] = {false, false, false, false, false};
+    if (GENERIC && a.vali != nullptr) {
+        ext_on[0] = a.B.tsurf != 0; ext_on[1] = a.B.alb != 0; ext_on[2] = a.B.smb != 0;
+        ext_on[3] = a.B.melt != 0;  ext_on[4] = a.B.acc != 0;
+    }
+
+    if (warp == kConsumerWarps) {
+        // ---------------- producer: one lane feeds the ring with TMA bulk copies ----------------
+        if (lane == 0) {
+            uint32_t nbytes = kForcingRows * T * (uint32_t)sizeof(double);
+            if (GENERIC) for (int e = 0; e < kExtRows; ++e) if (ext_on[e]) nbytes += T * (uint32_t)sizeof(double);
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+                const long long p0 = (long long)tile * T;
+                int fd = a.f_day0 % a.f_nwin;
+                for (int d = 0; d < a.ndays; ++d) {
+                    mbar_wait(&empty[stage], phase ^ 1u);
+                    mbar_expect_tx(&full[stage], nbytes);
+                    double *dst = sbuf + (size_t)stage * ROWS * T;
+                    const double *src = a.forcing + (long long)fd * a.f_day_stride + p0;
+#pragma unroll
+                    for (int v = 0; v < kForcingRows; ++v)
+                        tma_load_1d(dst + v * T, src + a.f_var_off[v], T * (uint32_t)sizeof(double), &full[stage]);
+                    if (GENERIC) {
+                        const double *vs = a.vali + (long long)fd * a.v_day_stride + p0;
+#pragma unroll
+                        for (int e = 0; e < kExtRows; ++e)
+                            if (ext_on[e])
+                                tma_load_1d(dst + (kForcingRows + e) * T, vs + c_ext_var[e] * a.v_var_stride,
+                                            T * (uint32_t)sizeof(double), &full[stage]);
+                    }
+                    if (++fd == a.f_nwin) fd = 0;
+                    if (++stage == NST) { stage = 0; phase ^= 1u; }
+                }
+            }
+        }
+        return;
+    }
+
+    // ---------------- consumers ----------------
+    const int tid = threadIdx.x;          // 0..255
+    const long long ld = a.ld;
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        const long long i0 = (long long)tile * T + (long long)tid * PPT;
+        Pt s[PPT];
+        bool valid[PPT];
+#pragma unroll
+        for (int p = 0; p < PPT; ++p) {
+            const long long i = i0 + p;
+            valid[p] = i < a.nx;
+            const long long ii = valid[p] ? i : 0;
+            const double *S = a.slab + ii;
+            s[p].mask = valid[p] ? a.mask[ii] : 0;
+            s[p].tsurf    = S[SEMIC_F_TSURF * ld];
+            s[p].hsnow    = S[SEMIC_F_HSNOW * ld];
+            s[p].hice     = S[SEMIC_F_HICE * ld];
+            s[p].alb      = S[SEMIC_F_ALB * ld];
+            s[p].alb_snow = S[SEMIC_F_ALB_SNOW * ld];
+            s[p].qmr_res  = S[SEMIC_F_QMR_RES * ld];
+            if (GENERIC) {
+                s[p].melt = S[SEMIC_F_MELT * ld];
+                s[p].melted_snow = S[SEMIC_F_MELTED_SNOW * ld];
+                s[p].melted_ice = S[SEMIC_F_MELTED_ICE * ld];
+                s[p].refr = S[SEMIC_F_REFR * ld];
+                s[p].smb = S[SEMIC_F_SMB * ld];
+                s[p].acc = S[SEMIC_F_ACC * ld];
+                s[p].lhf = S[SEMIC_F_LHF * ld];
+                s[p].shf = S[SEMIC_F_SHF * ld];
+                s[p].lwu = S[SEMIC_F_LWU * ld];
+                s[p].subl = S[SEMIC_F_SUBL * ld];
+                s[p].evap = S[SEMIC_F_EVAP * ld];
+                s[p].smb_snow = S[SEMIC_F_SMB_SNOW * ld];
+                s[p].smb_ice = S[SEMIC_F_SMB_ICE * ld];
+                s[p].runoff = S[SEMIC_F_RUNOFF * ld];
+                s[p].qmr = S[SEMIC_F_QMR * ld];
+                s[p].amp = S[SEMIC_F_AMP * ld];
+            } else {
+                s[p].melt = s[p].melted_snow = s[p].melted_ice = s[p].refr = s[p].smb = s[p].acc = 0.0;
+                s[p].lhf = s[p].shf = s[p].lwu = s[p].subl = s[p].evap = s[p].smb_snow = s[p].smb_ice = 0.0;
+                s[p].runoff = s[p].qmr = s[p].amp = 0.0;
+            }
+            s[p].t2m = 0.0;
+        }
+
+        for (int d = 0; d < a.ndays; ++d) {
+            mbar_wait(&full[stage], phase);
+            const double *row = sbuf + (size_t)stage * ROWS * T + tid * PPT;
+            const bool write_out = (a.out != nullptr) && (d >= a.out_start);
+            double *o = nullptr;
+            if (write_out) o = a.out + (long long)((d - a.out_start) % a.o_nring) * a.o_day_stride + i0;
+            double ov[SEMIC_NOUT + 1][PPT];
+#pragma unroll
+            for (int p = 0; p < PPT; ++p) {
+                if (valid[p]) {
+                    if (GENERIC) {                                     // example.f90:103-107
+                        if (ext_on[0]) s[p].tsurf = row[(kForcingRows + 0) * T + p];
+                        if (ext_on[1]) s[p].alb   = row[(kForcingRows + 1) * T + p];
+                        if (ext_on[2]) s[p].smb   = row[(kForcingRows + 2) * T + p];
+                        if (ext_on[3]) s[p].melt  = row[(kForcingRows + 3) * T + p];
+                        if (ext_on[4]) s[p].acc   = row[(kForcingRows + 4) * T + p];
+                    }
+                    double swd;
+                    const unsigned br = point_day<SCHEME, GENERIC>(s[p], row + p, T, a.P, a.B, a.eb_steps, a.do_mb, swd);
+                    ov[SEMIC_O_STT][p]   = s[p].tsurf;                 // example.f90:117-122
+                    ov[SEMIC_O_ALB][p]   = s[p].alb;
+                    ov[SEMIC_O_SWNET][p] = swd * (1.0 - s[p].alb);
+                    ov[SEMIC_O_SMB][p]   = s[p].smb;
+                    ov[SEMIC_O_MELT][p]  = s[p].melt;
+                    ov[SEMIC_O_ACC][p]   = s[p].acc;
+                    ov[SEMIC_O_SHF][p]   = s[p].shf;
+                    ov[SEMIC_O_LHF][p]   = s[p].lhf;
+                    ov[SEMIC_O_BRANCH][p] = (double)br;
+                } else {
+#pragma unroll
+                    for (int v = 0; v <= SEMIC_NOUT; ++v) ov[v][p] = 0.0;
+                }
+            }
+            // every shared-memory read of this stage is done: hand it back to the producer
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&empty[stage]);
+            if (++stage == NST) { stage = 0; phase ^= 1u; }
+
+            if (write_out) {
+                const int nv = a.o_nvar;
+                if (PPT == 2 && valid[PPT - 1]) {
+#pragma unroll
+                    for (int v = 0; v <= SEMIC_NOUT; ++v)
+                        if (v < nv) *reinterpret_cast<double2 *>(o + v * a.o_var_stride) = make_double2(ov[v][0], ov[v][PPT - 1]);
+                } else {
+#pragma unroll
+                    for (int p = 0; p < PPT; ++p)
+                        if (valid[p]) {
+#pragma unroll
+                            for (int v = 0; v <= SEMIC_NOUT; ++v)
+                                if (v < nv) o[v * a.o_var_stride + p] = ov[v][p];
+                        }
+                }
+            }
+        }
+
+        // final state of the tile: all 23 non-forcing fields, as after the reference's last call
+        if (a.ndays > 0) {
+#pragma unroll
+            for (int p = 0; p < PPT; ++p) {
+                if (!valid[p]) continue;
+                double *S = a.slab + (i0 + p);
+                S[SEMIC_F_T2M * ld] = s[p].t2m;
+                S[SEMIC_F_TSURF * ld] = s[p].tsurf;
+                S[SEMIC_F_HSNOW * ld] = s[p].hsnow;
+                S[SEMIC_F_HICE * ld] = s[p].hice;
+                S[SEMIC_F_ALB * ld] = s[p].alb;
+                S[SEMIC_F_ALB_SNOW * ld] = s[p].alb_snow;
+                S[SEMIC_F_MELT * ld] = s[p].melt;
+                S[SEMIC_F_MELTED_SNOW * ld] = s[p].melted_snow;
+                S[SEMIC_F_MELTED_ICE * ld] = s[p].melted_ice;
+                S[SEMIC_F_REFR * ld] = s[p].refr;
+                S[SEMIC_F_SMB * ld] = s[p].smb;
+                S[SEMIC_F_ACC * ld] = s[p].acc;
+                S[SEMIC_F_LHF * ld] = s[p].lhf;
+                S[SEMIC_F_SHF * ld] = s[p].shf;
+                S[SEMIC_F_LWU * ld] = s[p].lwu;
+                S[SEMIC_F_SUBL * ld] = s[p].subl;
+                S[SEMIC_F_EVAP * ld] = s[p].evap;
+                S[SEMIC_F_SMB_SNOW * ld] = s[p].smb_snow;
+                S[SEMIC_F_SMB_ICE * ld] = s[p].smb_ice;
+                S[SEMIC_F_RUNOFF * ld] = s[p].runoff;
+                S[SEMIC_F_QMR * ld] = s[p].qmr;
+                S[SEMIC_F_QMR_RES * ld] = s[p].qmr_res;
+                S[SEMIC_F_AMP * ld] = s[p].amp;
+            }
+        }
+    }
+}
+
+#if !SEMIC_STRICT
+// ------------------------------------------------------------------------------------------------
+// ensemble misfit (optimize/run_particles.f90:104-178 + utils.f90:23-42), config 5
+// ------------------------------------------------------------------------------------------------
+// A CTA is 32 points x 8 parameter sets ("particles"): lane = point, warp = particle, so parameters
+// are warp-uniform (read from shared memory) and the day's forcing/validation rows are shared by the
+// 8 warps through L1.  Every trajectory starts from the same initial slab (Q14), runs nloop x ntime
+// days and keeps one-pass shifted sums of d = model - validation for stt, melt, smb, swnet in the
+// last loop; crmsd^2 = (sum(e^2) - sum(e)^2/n)/n / var(validation).  Per-particle sums over the CTA's
+// 32 points go to partial[particle][tile] (fixed-order second stage: bitwise reproducible).
+constexpr int kEnsParticles = 8;
+
+__global__ void __launch_bounds__(32 * kEnsParticles) k_ensemble(const EnsArgs a, const int ngroups)
+{
+    __shared__ DevPar s_par[kEnsParticles];
+    const int tile = blockIdx.x / ngroups;
+    const int group = blockIdx.x % ngroups;
+    const int lane = threadIdx.x & 31;
+    const int warp = threadIdx.x >> 5;
+    const int p = group * kEnsParticles + warp;
+    const bool pvalid = p < a.npar;
+    {   // stage the CTA's parameter sets
+        const int nwords = (int)(sizeof(DevPar) / sizeof(double));
+        const double *src = reinterpret_cast<const double *>(a.pars + (pvalid ? p : 0));
+        double *dst = reinterpret_cast<double *>(&s_par[warp]);
+        for (int w = lane; w < nwords; w += 32) dst[w] = src[w];
+    }
+    __syncthreads();
+    const DevPar &P = s_par[warp];
+    const long long i = (long long)tile * 32 + lane;
+    const bool valid = pvalid && i < a.nx;
+    const long long ii = (i < a.nx) ? i : 0;
+    semic_bnd B;
+    B.t2m = B.tsurf = B.hsnow = B.alb = B.melt = B.refr = B.smb = B.acc = B.lhf = B.shf = B.subl = B.amp = 0;
+
+    Pt s;
+    const double *S = a.slab0 + ii;
+    const long long ld = a.ld;
+    s.mask = a.mask[ii];
+    s.tsurf = S[SEMIC_F_TSURF * ld];
+    s.hsnow = S[SEMIC_F_HSNOW * ld];
+    s.hice = S[SEMIC_F_HICE * ld];
+    s.alb = S[SEMIC_F_ALB * ld];
+    s.alb_snow = S[SEMIC_F_ALB_SNOW * ld];
+    s.qmr_res = S[SEMIC_F_QMR_RES * ld];
+    s.melt = s.melted_snow = s.melted_ice = s.refr = s.smb = s.acc = 0.0;
+    s.lhf = s.shf = s.lwu = s.subl = s.evap = s.smb_snow = s.smb_ice = s.runoff = s.qmr = s.amp = s.t2m = 0.0;
+
+    double d0[4] = {0, 0, 0, 0}, se[4] = {0, 0, 0, 0}, see[4] = {0, 0, 0, 0};
+    for (int k = 0; k < a.nloop; ++k) {
+        const bool lastloop = (k == a.nloop - 1);
+        for (int n = 0; n < a.ntime; ++n) {
+            const double *row = a.forcing + (long long)n * a.f_day_stride + ii;
+            double swd;
+            point_day<SCHEME_RUNTIME, false>(s, row, a.f_var_stride, P, B, P.n_ksub, 1, swd);
+            if (lastloop) {                                              // run_particles.f90:148-157
+                const double *v = a.vali + (long long)n * a.v_day_stride + ii;
+                double d[4];
+                d[0] = s.tsurf - v[SEMIC_O_STT * a.v_var_stride];
+                d[1] = s.melt - v[SEMIC_O_MELT * a.v_var_stride];
+                d[2] = s.smb - v[SEMIC_O_SMB * a.v_var_stride];
+                d[3] = swd * (1.0 - s.alb) - v[SEMIC_O_SWNET * a.v_var_stride];
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    if (n == 0) d0[q] = d[q];
+                    const double e = d[q] - d0[q];
+                    se[q] += e;
+                    see[q] = fma(e, e, see[q]);
+                }
+            }
+        }
+    }
+    // sum over the 4 variables of crmsd^2 (run_particles.f90:172-174)
+    double c = 0.0;
+    const double n = (double)a.ntime;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        const double var_d = fmax(0.0, (see[q] - se[q] * se[q] / n) / n);
+        c += var_d * a.inv_var[(long long)q * ld + ii];
+    }
+    if (!valid) c = 0.0;
+    // fixed-order warp tree
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) c += __shfl_down_sync(0xffffffffu, c, off);
+    if (lane == 0 && pvalid) a.partial[(long long)p * a.ntiles + tile] = c;
+}
+
+// 1/var of the validation series per point for stt, melt, smb, swnet (utils.f90:33-34: two-pass)
+__global__ void k_vali_invvar(const double *vali, long long day_stride, long long var_stride, int ntime, int nx, int ld,
+                              double *inv_var)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nx) return;
+    const int vars[4] = {SEMIC_O_STT, SEMIC_O_MELT, SEMIC_O_SMB, SEMIC_O_SWNET};
+    for (int q = 0; q < 4; ++q) {
+        const double *x = vali + vars[q] * var_stride + i;
+        double sum = 0.0;
+        for (int n = 0; n < ntime; ++n) sum += x[(long long)n * day_stride];
+        const double avg = sum / ntime;
+        double ss = 0.0;
+        for (int n = 0; n < ntime; ++n) { const double d = x[(long long)n * day_stride] - avg; ss += d * d; }
+        inv_var[(long long)q * ld + i] = 1.0 / (ss / ntime);
+    }
+}
+
+// second stage: sumsq[p] = sum over tiles, fixed order
+__global__ void k_ens_reduce(const double *partial, int ntiles, int npar, double *sumsq)
+{
+    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= npar) return;
+    double acc = 0.0;
+    for (int t = 0; t < ntiles; ++t) acc += partial[(long long)p * ntiles + t];
+    sumsq[p] = acc;
+}
+#endif  // !SEMIC_STRICT
+
+#undef BND
+
+}  // namespace SEMIC_MODE_NS
+}  // namespace semic

@@ -1,0 +1,89 @@
+// Fast arithmetic instantiation (the benchmarked path): FMA contraction, reciprocal multiplies,
+// MUFU-seeded division, custom exp.  Parity bar: 1e-10 relative per variable after one year.
+#define SEMIC_STRICT 0
+#define SEMIC_MODE_NS fast_mode
+#include <cstdlib>
+#include "semic_kernels.cuh"
+
+namespace semic {
+namespace fast_mode {
+#include "semic_launch.inl"
+
+// public elementals evaluated over arrays (surface_physics.f90:378-438)
+__global__ void k_elementals(int which, const double *in0, const double *in1, const double *in2, const double *in3,
+                             const double *in4, const int *mask, double s0, double s1, double s2, double s3,
+                             double *o0, double *o1, double *o2, int n)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    (void)mask;                                            // unused by the reference as well (:404)
+    if (which == 0) {
+        o0[i] = sensible_heat_flux(in0[i], in1[i], in2[i], in3[i], s0, s1);
+    } else if (which == 1) {
+        const double ts = in0[i], wind = in1[i], shum = in2[i], sp = in3[i], rho = in4[i];
+        const bool ice = ts < c_t0;
+        const double es = esat(ts, ice);
+        const double shum_sat = fdiv(es * s1, (es * (s1 - 1.0)) + sp);
+        const double q = ((s0 * wind) * rho) * (shum_sat - shum);
+        o0[i] = q * (ice ? s2 : s3);
+        o1[i] = ice ? q : 0.0;
+        o2[i] = ice ? 0.0 : q;
+    } else {
+        o0[i] = longwave_upward(in0[i], s0);
+    }
+}
+}  // namespace fast_mode
+
+cudaError_t launch_run_fast(const RunArgs &a, bool generic, int ppt, cudaStream_t st, int *launches)
+{
+    if (launches) ++*launches;
+    if (generic) return fast_mode::launch_scheme<true, 1, 1>(a, st);
+    // tuning knob: resident CTAs per SM the kernel is compiled for (register budget 65536/(288*MINB))
+    static int minb = -1;
+    if (minb < 0) {
+        const char *e = getenv("SEMIC_MINB");
+        minb = e ? atoi(e) : 2;
+        if (minb < 1 || minb > 3) minb = 2;
+    }
+    if (ppt == 2) {
+        if (minb >= 2) return fast_mode::launch_scheme<false, 2, 2>(a, st);
+        return fast_mode::launch_scheme<false, 2, 1>(a, st);
+    }
+    if (minb == 1) return fast_mode::launch_scheme<false, 1, 1>(a, st);
+    if (minb == 3) return fast_mode::launch_scheme<false, 1, 3>(a, st);
+    return fast_mode::launch_scheme<false, 1, 2>(a, st);
+}
+
+cudaError_t launch_vali_invvar(const EnsArgs &a, double *inv_var, cudaStream_t st)
+{
+    if (a.nx <= 0) return cudaSuccess;
+    fast_mode::k_vali_invvar<<<(a.nx + 127) / 128, 128, 0, st>>>(a.vali, a.v_day_stride, a.v_var_stride, a.ntime, a.nx, a.ld,
+                                                                 inv_var);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_ensemble_fast(const EnsArgs &a, double *sumsq_dev, cudaStream_t st)
+{
+    if (a.nx <= 0 || a.npar <= 0) return cudaSuccess;
+    const int ngroups = (a.npar + fast_mode::kEnsParticles - 1) / fast_mode::kEnsParticles;
+    const long long nblocks = (long long)a.ntiles * ngroups;
+    if (nblocks > 0x7fffffffLL) return cudaErrorInvalidValue;
+    fast_mode::k_ensemble<<<(unsigned)nblocks, 32 * fast_mode::kEnsParticles, 0, st>>>(a, ngroups);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return e;
+    fast_mode::k_ens_reduce<<<(a.npar + 127) / 128, 128, 0, st>>>(a.partial, a.ntiles, a.npar, sumsq_dev);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_elementals_fast(int which, const double *const *in, const int *mask, const double *sc,
+                                   double *const *out, int n, cudaStream_t st)
+{
+    const double *i0 = in[0], *i1 = nullptr, *i2 = nullptr, *i3 = nullptr, *i4 = nullptr;
+    double *o0 = out[0], *o1 = nullptr, *o2 = nullptr;
+    double s0 = sc[0], s1 = 0, s2 = 0, s3 = 0;
+    if (which == 0) { i1 = in[1]; i2 = in[2]; i3 = in[3]; s1 = sc[1]; }
+    if (which == 1) { i1 = in[1]; i2 = in[2]; i3 = in[3]; i4 = in[4]; s1 = sc[1]; s2 = sc[2]; s3 = sc[3]; o1 = out[1]; o2 = out[2]; }
+    fast_mode::k_elementals<<<(n + 255) / 256, 256, 0, st>>>(which, i0, i1, i2, i3, i4, mask, s0, s1, s2, s3, o0, o1, o2, n);
+    return cudaGetLastError();
+}
+}  // namespace semic

@@ -1,0 +1,415 @@
+"""Parity of the CUDA path (through the C-ABI / the SurfacePhysics module) against the CPU oracle.
+
+Bar (BASELINE.json north_star): FP64 state within 1e-10 relative per variable after one simulated year, with
+melt/refreeze threshold flips counted and reported: point-days at or after a point's first branch flip are left
+out of the 1e-10 statistic and bounded separately.
+"""
+import numpy as np
+import pytest
+
+from tests import util
+from tests.util import TOL
+
+pytestmark = pytest.mark.gpu
+
+
+def _gpu():
+    from tests import gpu_util
+    return gpu_util
+
+
+def _compare(par_d, bnd_names, forcing, ndays, mask, vali=None, strict=False, ppt=0, hsnow=1.0, tol=TOL,
+             max_flip_frac=2e-4, label=""):
+    g = _gpu()
+    nx = forcing.shape[2]
+    S0, m0 = util.init_slab(nx, mask, hsnow=hsnow)
+    fin_g, out_g, br_g, _ = g.run_gpu(S0, m0, par_d, bnd_names, forcing, ndays, vali=vali, out_days=ndays,
+                                      strict=strict, ppt=ppt)
+    fin_o, out_o, br_o = g.run_oracle(S0, m0, par_d, bnd_names, forcing, ndays, vali=vali, out_days=ndays)
+    nflip, pts, first = util.flip_report(br_g, br_o)
+    taint = util.tainted(br_g, br_o)
+    oe = util.out_errors(out_g, out_o, exclude=taint)
+    se = util.state_errors(fin_g, fin_o, exclude_points=pts)
+    pw = max(util.out_errors(out_g, out_o, exclude=taint, pointwise=True).values())
+    worst = max(list(oe.values()) + list(se.values()))
+    print("\n[parity %s] nx=%d days=%d k=%d scheme=%s strict=%d: max rel err %.3e (daily %s; pointwise+floor %.1e); "
+          "material flips: %d point-days on %d points (%.4f%% of point-days tainted); by bit %s"
+          % (label, nx, ndays, par_d["n_ksub"], par_d["alb_scheme"], strict, worst, max(oe, key=oe.get), pw,
+             nflip, int(pts.sum()), 100.0 * taint.mean(), util.flips_by_bit(br_g, br_o)))
+    assert worst <= tol, (oe, se)
+    # the pointwise metric is ill-conditioned near cancellations (tmean -> -amp, ts -> t2m); keep it bounded anyway
+    assert pw <= 1e-6, pw
+    # Flips are threshold events of single points (a one-ulp ghost snow layer over land keeps the :201 gate on),
+    # never a systematic drift: ice points (mask 2) are immune, only land points near complete snow melt flip.
+    assert (mask[pts] == 1).all() or pts.sum() <= max(2, int(max_flip_frac * nx)), (mask[pts], pts.sum())
+    assert taint.mean() <= 0.2, "too many tainted point-days: %.3f" % taint.mean()
+    return worst
+
+
+# ------------------------------------------------------------------------------------------------------------
+# shipped forcing (reference fixtures), all schemes, both arithmetic modes
+# ------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("strict", [False, True])
+@pytest.mark.parametrize("scheme", ["none", "slater", "isba", "denby", "alex", "unknown"])
+@pytest.mark.parametrize("k", [3, 24])
+def test_transect_one_year(scheme, k, strict):
+    forc, _ = util.load_fixture("transect")
+    par = dict(util.SCHEME_PARS[scheme], n_ksub=k)
+    mask = np.array([1, 1, 1, 2, 2, 2, 2], dtype=np.int32)          # example.namelist:5
+    _compare(par, (), forc, 365, mask, strict=strict, label="transect")
+
+
+def test_example_namelist_config1():
+    """config 1 (example/example.f90 with example.namelist): 100 loops x 365 days, k=3, scheme none."""
+    forc, _ = util.load_fixture("transect")
+    mask = np.array([1, 1, 1, 2, 2, 2, 2], dtype=np.int32)
+    g = _gpu()
+    S0, m0 = util.init_slab(7, mask, hsnow=5.0, alb=np.float64(np.float32(0.8)))    # Q9: single-precision literal
+    ndays = 36500
+    fin_g, out_g, br_g, _ = g.run_gpu(S0, m0, util.PAR_EXAMPLE, (), forc, ndays, out_days=365)
+    fin_o, out_o, br_o = g.run_oracle(S0, m0, util.PAR_EXAMPLE, (), forc, ndays, out_days=365)
+    taint = util.tainted(br_g, br_o)
+    oe = util.out_errors(out_g, out_o, exclude=taint)
+    print("\n[config1] 100 loops: ", {k: "%.2e" % v for k, v in oe.items()}, "flips in last year:", int((br_g != br_o).sum()))
+    assert max(oe.values()) <= TOL
+    # SURVEY 8(c) tripwire: annual-mean tsurf after 100 loops (computed with alb = 0.8 double; Q9 changes the 9th digit)
+    trip = np.array([263.14700780751525, 264.47640866970573, 264.87997270472795, 260.740161399957,
+                     258.08253199255205, 256.8596580925506, 255.56860129142902])
+    assert np.abs(out_g[:, 0, :].mean(axis=0) - trip).max() < 1e-5
+
+
+def test_c20_ten_years():
+    """c20 station: 3652 days of real forcing, single point (mask 2)."""
+    forc, _ = util.load_fixture("c20")
+    _compare(dict(util.PAR_SLATER, n_ksub=3), (), forc, forc.shape[0], np.array([2], dtype=np.int32), label="c20")
+
+
+# ------------------------------------------------------------------------------------------------------------
+# synthetic forcing generated on the device (the bench's generator): oracle consumes the same bytes
+# ------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("k,ppt", [(3, 1), (24, 1), (3, 2)])
+def test_synthetic_one_year(k, ppt):
+    from semic_b200 import engine
+    nx = 4096 + 333                       # several tiles, ragged tail
+    fs = engine.Series(nx, 9, 365).synth_forcing(20260101, point0=0, dayofs=0)
+    forc = fs.download()
+    fs.free()
+    r = np.random.default_rng(5)
+    mask = r.choice(np.array([2, 1, 0], dtype=np.int32), size=nx, p=[0.85, 0.10, 0.05]).astype(np.int32)
+    _compare(dict(util.PAR_SLATER, n_ksub=k), (), forc, 365, mask, ppt=ppt, label="synthetic")
+
+
+def test_synthetic_statistics():
+    """the device generator stays inside the ranges of SURVEY 8(d) / the shipped forcing"""
+    from semic_b200 import engine
+    fs = engine.Series(3000, 9, 365).synth_forcing(20260101, point0=12345, dayofs=0)
+    f = fs.download()
+    fs.free()
+    sf, rf, swd, lwd, wind, sp, rhoa, qq, t2m = [f[:, v, :] for v in range(9)]
+    assert np.isfinite(f).all()
+    assert sf.min() >= 0 and rf.min() >= 0 and 0.2 < (sf == 0).mean() < 0.95
+    assert swd.min() == 0 and 300 < swd.max() <= 400 and 80 < swd.mean() < 200
+    assert lwd.min() >= 70 and lwd.max() <= 340
+    assert wind.min() >= 0.1 and wind.max() <= 22
+    assert 55000 < sp.min() and sp.max() < 108000
+    assert 0.7 < rhoa.min() and rhoa.max() < 1.8
+    assert 0 < qq.min() and qq.max() < 2e-2
+    assert 200 < t2m.min() and t2m.max() < 300
+    # counter based: a shifted window reproduces the same values
+    fs2 = engine.Series(1000, 9, 100).synth_forcing(20260101, point0=12345 + 500, dayofs=50)
+    f2 = fs2.download()
+    fs2.free()
+    assert np.array_equal(f2, f[50:150, :, 500:1500])
+
+
+# ------------------------------------------------------------------------------------------------------------
+# boundary overrides (generic kernel): example.f90:103-107 feeds tsurf/alb/melt/acc/smb from the validation file
+# ------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("strict", [False, True])
+@pytest.mark.parametrize("names", [("tsurf",), ("alb",), ("tsurf", "alb"), ("melt",), ("acc", "smb"), ("shf", "lhf"),
+                                   ("refr",), ("amp",), ("t2m", "hsnow", "subl", "massbal")])
+def test_boundary_overrides_isba(names, strict):
+    forc, vali = util.load_fixture("transect")
+    mask = np.array([1, 1, 1, 2, 2, 2, 2], dtype=np.int32)
+    g = _gpu()
+    S0, m0 = util.init_slab(7, mask)
+    S0[util.ob.FIDX["amp"]] = 2.5          # consulted when bnd%amp
+    S0[util.ob.FIDX["shf"]] = 3.0          # frozen when bnd%shf
+    S0[util.ob.FIDX["lhf"]] = -2.0
+    S0[util.ob.FIDX["subl"]] = 1e-9        # divided by rhow every sub-step under bnd%lhf (Q3)
+    S0[util.ob.FIDX["refr"]] = 1e-9
+    S0[util.ob.FIDX["smb_snow"]] = 2e-9    # frozen when bnd%smb
+    par = dict(util.PAR_ISBA, n_ksub=3)
+    fin_g, out_g, br_g, _ = g.run_gpu(S0, m0, par, names, forc, 365, vali=vali, out_days=365, strict=strict)
+    fin_o, out_o, br_o = g.run_oracle(S0, m0, par, names, forc, 365, vali=vali, out_days=365)
+    taint = util.tainted(br_g, br_o)
+    oe = util.out_errors(out_g, out_o, exclude=taint)
+    se = util.state_errors(fin_g, fin_o, exclude_points=taint.any(axis=0))
+    print("\n[bnd %s strict=%d] daily %.2e state %.2e flips %d" % (",".join(names), strict, max(oe.values()),
+                                                                    max(se.values()), int((br_g != br_o).sum())))
+    assert max(oe.values()) <= TOL and max(se.values()) <= TOL
+
+
+# ------------------------------------------------------------------------------------------------------------
+# the drop-in daily call through the SurfacePhysics module (f2py/test.py call sequence)
+# ------------------------------------------------------------------------------------------------------------
+def test_dropin_daily_step_module_api(tmp_path):
+    import SurfacePhysics as sp
+    from oracle import binding as ob
+    forc, vali = util.load_fixture("transect")
+    nx, ntime = 7, 60
+    nml = tmp_path / "test.nml"
+    nml.write_text(open(util.GOLDEN + "/test_slater.nml").read())
+    par = sp.surface_physics.Surface_Param_Class()
+    sp.surface_physics.surface_physics_par_load(par, str(nml))
+    par.nx = nx
+    bnd = sp.surface_physics.Boundary_Opt_Class()
+    sp.surface_physics.surface_boundary_define(bnd, par.boundary)
+    state = sp.surface_physics.Surface_State_Class()
+    sp.surface_physics.surface_alloc(state, par.nx)
+    state.tsurf = np.array([vali[0, 0, i] for i in range(nx)])
+    state.hsnow = np.array([1.0 for i in range(nx)])
+    state.hice = np.array([0.0 for i in range(nx)])
+    state.alb = vali[0, 1, :]
+    state.alb_snow = vali[0, 1, :]
+    state.mask = np.array([2 for i in range(nx)])
+    state.mask[0:3] = 1
+    # oracle twin
+    S, m = ob.new_state(nx)
+    for n in ("tsurf", "hsnow", "hice", "alb", "alb_snow"):
+        S[ob.FIDX[n]] = getattr(state, n)
+    m[:] = state.mask
+    opar = ob.make_par(dict(util.PAR_SLATER, rcrit=par.rcrit, n_ksub=par.n_ksub))
+    obnd = ob.make_bnd()
+    names9 = ["sf", "rf", "swd", "lwd", "wind", "sp", "rhoa", "qq", "t2m"]
+    worst = 0.0
+    for t in range(ntime):
+        for v, n in enumerate(names9):
+            setattr(state, n, forc[t, v, :])
+            S[ob.FIDX[n]] = forc[t, v, :]
+        sp.surface_physics.surface_energy_and_mass_balance(state, par, bnd, t, 0)
+        ob.step(S, m, opar, obnd)
+        e = util.state_errors(state.as_slab(), S)
+        worst = max(worst, max(e.values()))
+    print("\n[drop-in] 60 daily calls, all 23 fields every day: max rel err %.3e" % worst)
+    assert worst <= TOL
+    sp.surface_physics.surface_dealloc(state)
+
+
+def test_energy_and_mass_balance_separately():
+    """energy_balance / mass_balance are public module procedures (surface_physics.f90:122)."""
+    from oracle import binding as ob
+    import ctypes as C
+    g = _gpu()
+    from semic_b200 import surface_physics as spm
+    forc, _ = util.load_fixture("transect")
+    mask = np.array([1, 1, 0, 2, 2, 2, 2], dtype=np.int32)
+    S0, m0 = util.init_slab(7, mask, tsurf=272.9)
+    names9 = ["sf", "rf", "swd", "lwd", "wind", "sp", "rhoa", "qq", "t2m"]
+    for v, n in enumerate(names9):
+        S0[ob.FIDX[n]] = forc[180, v, :]
+    par_d = dict(util.PAR_SLATER, n_ksub=3)
+    st = g.make_state(S0, m0)
+    par, bnd = g.make_par(par_d), g.make_bnd()
+    S = S0.copy()
+    now = ob.OraclePar  # noqa: F841
+    opar, obnd = ob.make_par(par_d), ob.make_bnd()
+    import oracle.binding as b
+    L = b.lib()
+
+    class OS(C.Structure):
+        _fields_ = [("nx", C.c_int), ("ld", C.c_int), ("slab", C.POINTER(C.c_double)), ("mask", C.POINTER(C.c_int)),
+                    ("branch", C.POINTER(C.c_ubyte))]
+    os_ = OS(7, 7, S.ctypes.data_as(C.POINTER(C.c_double)), m0.ctypes.data_as(C.POINTER(C.c_int)), None)
+    L.oracle_energy_balance.argtypes = [C.POINTER(OS), C.POINTER(b.OraclePar), C.POINTER(b.OracleBnd)]
+    L.oracle_mass_balance.argtypes = [C.POINTER(OS), C.POINTER(b.OraclePar), C.POINTER(b.OracleBnd)]
+    for it in range(4):
+        spm.energy_balance(st, par, bnd, 1, 0)
+        L.oracle_energy_balance(C.byref(os_), C.byref(opar), C.byref(obnd))
+        e = util.state_errors(st.as_slab(), S)
+        assert max(e.values()) <= TOL, ("energy_balance", it, e)
+    spm.mass_balance(st, par, bnd, 1, 0)
+    L.oracle_mass_balance(C.byref(os_), C.byref(opar), C.byref(obnd))
+    e = util.state_errors(st.as_slab(), S)
+    assert max(e.values()) <= TOL, ("mass_balance", e)
+    spm.surface_dealloc(st)
+
+
+# ------------------------------------------------------------------------------------------------------------
+# elementals: known-answer tests evaluated by the device functions
+# ------------------------------------------------------------------------------------------------------------
+def test_elementals_known_answers():
+    from semic_b200 import surface_physics as spm
+    from oracle import binding as ob
+    L = ob.lib()
+    assert abs(spm.longwave_upward(273.15, spm.sigm)[0] - 315.63697918226688) < 1e-10
+    ts = np.linspace(215., 290., 301)
+    lw = spm.longwave_upward(ts, spm.sigm)
+    assert np.abs(lw / np.array([L.oracle_longwave_upward(t, spm.sigm) for t in ts]) - 1).max() < 1e-14
+    shf = spm.sensible_heat_flux(ts, ts + 1.5, 6.0, 1.2, 2e-3, spm.cap)
+    ref = np.array([L.oracle_sensible_heat_flux(t, t + 1.5, 6.0, 1.2, 2e-3, spm.cap) for t in ts])
+    assert np.abs(shf - ref).max() <= 1e-12 * np.abs(ref).max()
+    lhf, subl, evap = spm.latent_heat_flux(ts, 6.0, 1e-3, 90000., 1.2, 2, 5e-4, spm.eps, spm.cls, spm.clv)
+    import ctypes as C
+    for i, t in enumerate(ts):
+        a, b_, c = C.c_double(), C.c_double(), C.c_double()
+        L.oracle_latent_heat_flux(t, 6.0, 1e-3, 90000., 1.2, 2, 5e-4, spm.eps, spm.cls, spm.clv, C.byref(a), C.byref(b_), C.byref(c))
+        assert abs(lhf[i] - a.value) <= 1e-12 * max(abs(a.value), 1.0)
+        assert abs(subl[i] - b_.value) <= 1e-12 * max(abs(b_.value), 1e-6)
+        assert abs(evap[i] - c.value) <= 1e-12 * max(abs(c.value), 1e-6)
+        assert (subl[i] == 0.0) == (t >= 273.15) or b_.value == 0.0
+    # at t0 both saturation formulas give 611.2 Pa: q = clh*wind*rho*(611.2*eps/(611.2*(eps-1)+sp) - shum)
+    lhf0, subl0, evap0 = spm.latent_heat_flux(273.15, 6.0, 0.0, 90000., 1.2, 2, 5e-4, spm.eps, spm.cls, spm.clv)
+    q = 5e-4 * 6.0 * 1.2 * (611.2 * spm.eps / (611.2 * (spm.eps - 1.0) + 90000.))
+    assert subl0[0] == 0.0 and abs(evap0[0] - q) < 1e-15 and abs(lhf0[0] - q * spm.clv) < 1e-9
+
+
+# ------------------------------------------------------------------------------------------------------------
+# edge cases: empty state, single point, ocean points, zero sub-steps
+# ------------------------------------------------------------------------------------------------------------
+def test_empty_and_single_point():
+    from semic_b200 import engine
+    from semic_b200 import surface_physics as spm
+    g = _gpu()
+    st = spm.Surface_State_Class()
+    spm.surface_alloc(st, 0)
+    par, bnd = g.make_par(util.PAR_SLATER), g.make_bnd()
+    spm.surface_energy_and_mass_balance(st, par, bnd, 1, 0)          # no-op on nx = 0
+    fs = engine.Series(0, 9, 3)
+    assert engine.run(st, par, bnd, fs, 3) == 0.0
+    fs.free()
+    spm.surface_dealloc(st)
+    forc, _ = util.load_fixture("c01")
+    _compare(dict(util.PAR_SLATER, n_ksub=3), (), forc, 365, np.array([2], dtype=np.int32), label="c01")
+
+
+def test_ocean_points_invariants():
+    forc = util.random_forcing(300, 120, seed=3)
+    mask = np.zeros(300, dtype=np.int32)
+    g = _gpu()
+    S0, m0 = util.init_slab(300, mask)
+    fin, out, br, _ = g.run_gpu(S0, m0, util.PAR_SLATER, (), forc, 120, out_days=120)
+    from oracle import binding as ob
+    assert (fin[ob.FIDX["hsnow"]] == 0).all() and (fin[ob.FIDX["alb"]] == 0.06).all()
+    assert (fin[ob.FIDX["qmr_res"]] == 0).all() and (out[:, 4, :] == 0).all()
+
+
+def test_errors_are_loud(tmp_path):
+    from semic_b200 import surface_physics as spm
+    from semic_b200 import SemicError
+    par = spm.Surface_Param_Class()
+    with pytest.raises(SemicError):
+        spm.surface_physics_par_load(par, str(tmp_path / "missing.nml"))
+    st = spm.Surface_State_Class()
+    with pytest.raises(SemicError):
+        spm.surface_energy_and_mass_balance(st, par, spm.Boundary_Opt_Class(), 1, 0)     # not allocated
+    a, b = spm.Surface_State_Class(), spm.Surface_State_Class()
+    spm.surface_alloc(a, 4)
+    spm.surface_alloc(b, 4)
+    with pytest.raises(SemicError):
+        spm.surface_physics_average(a, b, "bogus")
+    with pytest.raises(SemicError):
+        spm.surface_physics_average(a, b, "end")                                          # nt not provided
+    spm.surface_dealloc(a)
+    spm.surface_dealloc(b)
+
+
+def test_surface_physics_average():
+    from semic_b200 import surface_physics as spm
+    from oracle import binding as ob
+    r = np.random.default_rng(9)
+    nx = 1500
+    now, ave = spm.Surface_State_Class(), spm.Surface_State_Class()
+    spm.surface_alloc(now, nx)
+    spm.surface_alloc(ave, nx)
+    ref = np.zeros((31, nx))
+    spm.surface_physics_average(ave, now, "init")
+    L = ob.lib()
+    import ctypes as C
+    dp = lambda a: a.ctypes.data_as(C.POINTER(C.c_double))
+    for it in range(5):
+        slab = r.normal(size=(31, nx))
+        for n in ob.FIELDS:
+            setattr(now, n, slab[ob.FIDX[n]])
+        now.upload()
+        spm.surface_physics_average(ave, now, "step")
+        L.oracle_surface_physics_average(dp(ref), dp(slab), nx, nx, 1, 0.0)
+    spm.surface_physics_average(ave, now, "end", 5.0)
+    L.oracle_surface_physics_average(dp(ref), dp(slab), nx, nx, 2, 5.0)
+    ave.download()
+    assert np.array_equal(ave.as_slab(), ref)            # sums and one division: bit exact
+    spm.surface_dealloc(now)
+    spm.surface_dealloc(ave)
+
+
+# ------------------------------------------------------------------------------------------------------------
+# host-streamed run == device-resident run, bit for bit
+# ------------------------------------------------------------------------------------------------------------
+def test_run_host_equals_run():
+    from semic_b200 import engine
+    g = _gpu()
+    nx, nwin, ndays = 3000, 30, 75
+    forc = util.random_forcing(nx, nwin, seed=11)
+    mask = np.full(nx, 2, dtype=np.int32)
+    mask[::7] = 1
+    S0, m0 = util.init_slab(nx, mask)
+    fin_a, out_a, _, _ = g.run_gpu(S0, m0, util.PAR_SLATER, (), forc, ndays, out_days=40, branch=False)
+    st = g.make_state(S0, m0)
+    par, bnd = g.make_par(util.PAR_SLATER), g.make_bnd()
+    hf = engine.PinnedArray((nwin, 9, nx))
+    hf.array[...] = forc
+    ho = engine.PinnedArray((40, 8, nx))
+    ms = engine.run_host(st, par, bnd, hf.array, ndays, h_out=ho.array, out_days=40, chunk_days=8)
+    st.download()
+    assert ms > 0
+    fin_b = st.as_slab()
+    assert np.array_equal(fin_a[:23], fin_b[:23])
+    assert np.array_equal(out_a, ho.array)
+    from semic_b200 import surface_physics as spm
+    spm.surface_dealloc(st)
+    hf.free()
+    ho.free()
+
+
+# ------------------------------------------------------------------------------------------------------------
+# size-independent properties at large N (BASELINE sizes are too big for the oracle)
+# ------------------------------------------------------------------------------------------------------------
+def test_large_grid_properties():
+    from semic_b200 import engine
+    from semic_b200 import surface_physics as spm
+    from oracle import binding as ob
+    g = _gpu()
+    nx, nwin, ndays = 2_000_003, 10, 25
+    par, bnd = g.make_par(dict(util.PAR_SLATER, n_ksub=3)), g.make_bnd()
+
+    def run_shard(p0, n):
+        st = spm.Surface_State_Class()
+        spm.surface_alloc(st, n)
+        from semic_b200._capi import lib, check
+        check(lib().semic_state_synth_mask(st.handle, 7, p0, 0.85, 0.10))
+        for name, v in (("tsurf", 260.), ("hsnow", 1.0), ("alb", 0.8), ("alb_snow", 0.8)):
+            check(lib().semic_state_fill(st.handle, ob.FIDX[name], v))
+        fs = engine.Series(n, 9, nwin).synth_forcing(20260101, point0=p0, dayofs=0)
+        outs = engine.Series(n, 8, 4)
+        engine.run(st, par, bnd, fs, ndays, out=outs, out_days=4)
+        st.download()
+        fin = st.as_slab()
+        mask = np.array(st.mask)
+        o = outs.download()
+        fs.free(); outs.free(); spm.surface_dealloc(st)
+        return fin, o, mask
+
+    fin, out, mask = run_shard(0, nx)
+    # invariants of the scheme
+    hs = fin[ob.FIDX["hsnow"]]
+    assert np.isfinite(fin[:23]).all() and hs.min() >= 0.0 and hs.max() <= 5.0
+    ice = mask == 2
+    assert np.array_equal(fin[ob.FIDX["melt"]][ice], (fin[ob.FIDX["melted_snow"]] + fin[ob.FIDX["melted_ice"]])[ice])
+    oc = mask == 0
+    assert (hs[oc] == 0).all() and (fin[ob.FIDX["alb"]][oc] == 0.06).all() and (fin[ob.FIDX["qmr_res"]][oc] == 0).all()
+    assert (fin[ob.FIDX["tsurf"]][ice] <= 273.15).all()
+    # sharding invariance: any contiguous shard reproduces its slice of the full run bit for bit
+    p0, n = 777_777, 300_001
+    fin_s, out_s, _ = run_shard(p0, n)
+    assert np.array_equal(fin_s[:23], fin[:23, p0:p0 + n])
+    assert np.array_equal(out_s, out[:, :, p0:p0 + n])
