@@ -1,0 +1,405 @@
+#!/usr/bin/env python
+"""bench.py -- grid-point-days/s of the SEMIC time step on B200 (BASELINE.json metric).
+
+  python bench.py --gpus N --steps K --warmup W          # our arm (CUDA, through the C-ABI)
+  python bench.py --impl reference --gpus N ...          # the reference's CPU implementation (oracle port)
+
+Workload (config.workload): BASELINE.json configs[2] -- synthetic Antarctica-scale grid, 16 777 216 points per
+GPU, slater albedo, daily forcing [day][9][point] resident in HBM as a periodic window; a STEP is one simulated
+year (365 days) of `surface_energy_and_mass_balance` over every point, with the 8 daily output fields the
+reference drivers emit written to a ring (output mode M1, 136 algorithmic bytes per point-day).  `--steps 10`
+is the 10-year run.  Grid points are sharded contiguously over the ranks with no communication ("weak": every
+rank owns --points points).
+
+One JSON line on stdout (rank 0).  See DESIGN.md "Measurement" for the definition of every key.
+"""
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+
+SEED = 20260101
+B_FORCING = 72          # 9 doubles read per point-day
+B_OUT = 64              # 8 doubles written per point-day (M1)
+PAR_SLATER = dict(tstic=86400., ceff=2.0e6, csh=2.0e-3, clh=5.0e-4, alb_smax=0.80, alb_smin=0.77, albi=0.45,
+                  albl=0.15, tmin=263.15, tmax=273.15, hcrit=0.09, rcrit=0.5, amp=3.1, alb_scheme="slater",
+                  tau_a=0.008, tau_f=0.24, w_crit=15.0, mcrit=6.0e-8, afac=-0.18, tmid=275.35)
+SCHEME_OVERRIDES = {"isba": dict(alb_smin=0.6, alb_smax=0.85), "denby": dict(alb_smin=0.6, alb_smax=0.85),
+                    "alex": dict(alb_smin=0.6, alb_smax=0.85), "none": {}, "slater": {}}
+
+
+def par_dict(scheme, k):
+    d = dict(PAR_SLATER, alb_scheme=scheme, n_ksub=k)
+    d.update(SCHEME_OVERRIDES.get(scheme, {}))
+    return d
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return json.load(open(p)), "measured (MEASURED_PEAKS.json)"
+        except Exception:
+            pass
+    return {"hbm_gbs": 6650.0}, "fallback (B200_PROFILING.md: 6.65 TB/s)"
+
+
+class ClockSampler(object):
+    """nvidia-smi clocks/throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.proc = None
+        self.lines = []
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(gpu_index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._pump, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for ln in self.proc.stdout:
+            self.lines.append(ln.strip())
+
+    def mark(self):
+        return len(self.lines)
+
+    def stop(self, lo=0, hi=None):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        time.sleep(0.15)
+        try:
+            self.proc.terminate()
+            self.proc.wait(timeout=5)
+        except Exception:
+            pass
+        rows = [l.split(",") for l in self.lines[lo:hi] if l.count(",") >= 6]
+        sm, mx, pw, reasons = [], [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in rows:
+            try:
+                sm.append(float(r[0])); mx.append(float(r[1])); pw.append(float(r[2]))
+            except ValueError:
+                continue
+            for n, v in zip(names, r[3:7]):
+                if v.strip().lower().startswith("active"):
+                    reasons.add(n)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "power_w_max": max(pw) if pw else None, "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# CPU arm: the oracle port of the reference, one thread per host core (ctypes releases the GIL)
+# ---------------------------------------------------------------------------------------------------------------
+def cpu_reference_rate(scheme, k, pts_per_core, ndays, reps, cores=None):
+    """Times oracle_run (array-form restatement of surface_physics.f90) on cores x pts_per_core points x ndays days.
+    Returns (point-days/s, cores, seconds of the best repetition)."""
+    from oracle import binding as ob
+    from semic_b200 import synth
+    cores = cores or os.cpu_count() or 1
+    nwin = min(ndays, 73)
+    stride = 5 if nwin == 73 else 1
+    par = ob.make_par(par_dict(scheme, k))
+    bnd = ob.make_bnd()
+    ob.lib()
+    forc = [np.ascontiguousarray(synth.forcing(pts_per_core, nwin, SEED, point0=c * pts_per_core, daystride=stride)) for c in range(min(cores, 4))]
+    jobs = []
+    for c in range(cores):
+        S, m = ob.new_state(pts_per_core)
+        m[:] = synth.mask(pts_per_core, 7, c * pts_per_core, 0.97, 0.02)
+        S[ob.FIDX["tsurf"]] = 260.0
+        S[ob.FIDX["hsnow"]] = 1.0
+        S[ob.FIDX["alb"]] = 0.8
+        S[ob.FIDX["alb_snow"]] = 0.8
+        jobs.append((S, m, forc[c % len(forc)], np.zeros((8, 8, pts_per_core))))
+
+    def work(j):
+        S, m, f, out = j
+        dp = lambda a: a.ctypes.data_as(C.POINTER(C.c_double))
+        ob.lib().oracle_run(dp(S), S.shape[1], m.ctypes.data_as(C.POINTER(C.c_int)), S.shape[1], C.byref(par),
+                            C.byref(bnd), dp(f), None, f.shape[0], f.shape[2], ndays, dp(out), 8, pts_per_core, ndays, None)
+
+    best = None
+    for _ in range(reps):
+        th = [threading.Thread(target=work, args=(j,)) for j in jobs]
+        t0 = time.perf_counter()
+        for t in th:
+            t.start()
+        for t in th:
+            t.join()
+        dt = time.perf_counter() - t0
+        best = dt if best is None else min(best, dt)
+    return cores * pts_per_core * ndays / best, cores, best
+
+
+def run_reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    k = args.n_ksub
+    pts = args.cpu_points_per_core
+    for _ in range(args.warmup):
+        cpu_reference_rate(args.scheme, k, pts, min(args.cpu_days, 30), 1)
+    t0 = time.perf_counter()
+    rates = []
+    for _ in range(args.steps):
+        r, cores, sec = cpu_reference_rate(args.scheme, k, pts, args.cpu_days, 1)
+        rates.append(r)
+    wall = time.perf_counter() - t0
+    cores = os.cpu_count() or 1
+    value = float(np.mean(rates))
+    sample = "%d cores x %d points x %d days per step (array-form C oracle, gcc -O3 -fno-fast-math)" % (cores, pts, args.cpu_days)
+    line = {"impl": "reference", "metric": "grid-point-days/s", "value": value, "unit": "point-days/s",
+            "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": 1e3 * wall / max(args.steps, 1), "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": workload_config(args, 1),
+            "cpu_baseline": {"value": value, "unit": "point-days/s", "cores": cores, "kind": "port", "sample": sample},
+            "e2e": {"value": value, "unit": "point-days/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line))
+    return 0
+
+
+def workload_config(args, world):
+    return {"workload": "C3 synthetic Antarctica-scale grid: %d points/GPU x 365 days/step, slater-family scheme '%s', "
+                        "n_ksub=%d, daily output M1 (8 fields), forcing window %d days resident in HBM"
+                        % (args.points, args.scheme, args.n_ksub, args.window),
+            "points_per_gpu": args.points, "days_per_step": args.days, "n_ksub": args.n_ksub, "alb_scheme": args.scheme,
+            "forcing_window_days": args.window, "forcing_window_stride_days": args.window_stride, "output_ring_days": args.ring, "output_mode": "M1",
+            "sharding": "contiguous point ranges, no communication", "world_size": world,
+            "l2": "inputs (forcing window) far larger than the 126 MB L2; every byte is read once per pass",
+            "seed": SEED}
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# GPU arm
+# ---------------------------------------------------------------------------------------------------------------
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--points", type=int, default=1 << 24, help="grid points per GPU (C3: 16 777 216)")
+    ap.add_argument("--days", type=int, default=365, help="simulated days per step")
+    ap.add_argument("--n-ksub", type=int, default=3, help="sub-daily steps (the reference's shipped namelists use 3)")
+    ap.add_argument("--scheme", default="slater")
+    ap.add_argument("--window", type=int, default=73, help="periodic forcing window resident in HBM (days)")
+    ap.add_argument("--window-stride", type=int, default=5, help="window row w holds calendar day w*stride (73 x 5 = one year)")
+    ap.add_argument("--ring", type=int, default=32, help="daily-output ring (days); large enough that the ring is not L2-resident")
+    ap.add_argument("--ppt", type=int, default=0)
+    ap.add_argument("--e2e-days", type=int, default=8, help="days per end-to-end (host buffers) step")
+    ap.add_argument("--e2e-steps", type=int, default=2)
+    ap.add_argument("--cpu-points-per-core", type=int, default=8192)
+    ap.add_argument("--cpu-days", type=int, default=365)
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--extra", action="store_true", help="also time C2 (100k points, n_ksub=24) and C3 at n_ksub=24")
+    args = ap.parse_args()
+
+    if args.impl == "reference":
+        return run_reference_arm(args)
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    dist = None
+    if world > 1:
+        import torch
+        import torch.distributed as dist
+        torch.cuda.set_device(local_rank)
+        dist.init_process_group("nccl")
+
+    from semic_b200 import engine
+    from semic_b200 import surface_physics as sp
+    from semic_b200._capi import FIELD_ID, check, lib
+    engine.set_device(local_rank)
+    L = lib()
+
+    def barrier():
+        check(L.semic_device_synchronize())
+        if dist is not None:
+            import torch
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    def make_par(k, scheme):
+        par = sp.Surface_Param_Class()
+        for key, v in par_dict(scheme, k).items():
+            setattr(par, key, v)
+        par.tsticsub = par.tstic / float(k)
+        return par
+
+    def make_state(n, p0, frac_ice=0.97, frac_land=0.02):
+        st = sp.Surface_State_Class()
+        sp.surface_alloc(st, n)
+        check(L.semic_state_synth_mask(st.handle, 7, p0, frac_ice, frac_land))      # Antarctica-like 97/2/1
+        for name, v in (("tsurf", 260.0), ("hsnow", 1.0), ("hice", 0.0), ("alb", 0.8), ("alb_snow", 0.8), ("qmr_res", 0.0)):
+            check(L.semic_state_fill(st.handle, FIELD_ID[name], v))
+        return st
+
+    N = args.points
+    p0 = rank * N
+    par = make_par(args.n_ksub, args.scheme)
+    bnd = sp.Boundary_Opt_Class()
+    st = make_state(N, p0)
+    forcing = engine.Series(N, 9, args.window).synth_forcing(SEED, point0=p0, dayofs=0, daystride=args.window_stride)
+    out = engine.Series(N, 8, args.ring)
+
+    def step(i):
+        return engine.run(st, par, bnd, forcing, args.days, day0=(i * args.days) % args.window, out=out,
+                          out_days=args.days, ppt=args.ppt)
+
+    for i in range(args.warmup):
+        step(i)
+    barrier()
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    time.sleep(0.3 if sampler else 0.0)
+    lo = sampler.mark() if sampler else 0
+    launches0 = engine.kernel_launches()
+    barrier()
+    t_wall0 = time.perf_counter()
+    kernel_ms = 0.0
+    for i in range(args.steps):
+        kernel_ms += step(args.warmup + i)
+    barrier()
+    wall_ms = 1e3 * (time.perf_counter() - t_wall0)
+    hi = sampler.mark() if sampler else 0
+    launches = engine.kernel_launches() - launches0
+    clocks = sampler.stop(lo, hi) if sampler else None
+
+    # max over ranks of the device time (CUDA events on the library's stream, summed over the K launches)
+    if dist is not None:
+        import torch
+        t = torch.tensor([kernel_ms, wall_ms], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        kernel_ms, wall_ms = float(t[0]), float(t[1])
+    ptdays_step = float(N) * args.days * world
+    value = ptdays_step * args.steps / (kernel_ms * 1e-3)
+
+    # ---- end to end: host (pinned) forcing -> H2D -> kernel -> D2H of the daily output, through semic_run_host ----
+    e2e = None
+    if not args.no_e2e:
+        wh = min(4, args.e2e_days)
+        hf = engine.PinnedArray((wh, 9, N))
+        fs = forcing.download(0, wh) if N <= (1 << 22) else None
+        if fs is not None:
+            hf.array[...] = fs
+        else:       # fill the pinned window piecewise to bound host memory
+            chunk = 1 << 21
+            for c0 in range(0, N, chunk):
+                c1 = min(N, c0 + chunk)
+                hf.array[:, :, c0:c1] = forcing.download(0, wh, c0, c1 - c0)
+        ho = engine.PinnedArray((args.e2e_days, 8, N))
+        engine.run_host(st, par, bnd, hf.array, min(args.e2e_days, 8), h_out=ho.array[:min(args.e2e_days, 8)],
+                        out_days=min(args.e2e_days, 8), chunk_days=2, ppt=args.ppt)
+        barrier()
+        tot = 0.0
+        for _ in range(args.e2e_steps):
+            tot += engine.run_host(st, par, bnd, hf.array, args.e2e_days, h_out=ho.array, out_days=args.e2e_days,
+                                   chunk_days=2, ppt=args.ppt)
+        barrier()
+        if dist is not None:
+            import torch
+            t = torch.tensor([tot], dtype=torch.float64, device="cuda")
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            tot = float(t[0])
+        e2e = {"value": float(N) * world * args.e2e_days * args.e2e_steps / (tot * 1e-3), "unit": "point-days/s",
+               "h2d_bytes_per_step": int(N) * args.e2e_days * B_FORCING * world,
+               "d2h_bytes_per_step": int(N) * args.e2e_days * B_OUT * world,
+               "days_per_step": args.e2e_days, "steps": args.e2e_steps,
+               "api": "semic_run_host (pinned host forcing window -> chunked H2D || kernel || D2H of the 8 daily fields)"}
+        hf.free()
+        ho.free()
+
+    if rank != 0:
+        if dist is not None:
+            dist.destroy_process_group()
+        return 0
+
+    peaks, peak_src = measured_peaks()
+    hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+    # dominant kernel = k_run (the only kernel in the timed region): algorithmic bytes per launch / mean launch time
+    launch_ms = kernel_ms / max(args.steps, 1)
+    alg_bytes = float(N) * args.days * (B_FORCING + B_OUT)
+    achieved = alg_bytes / (launch_ms * 1e-3) / 1e9
+    traffic = None
+    tp = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(tp):
+        try:
+            tj = json.load(open(tp))
+            key = "k%d" % args.n_ksub
+            if key in tj and tj[key].get("bytes_per_point_day") is not None:
+                traffic = tj[key]["bytes_per_point_day"] * float(N) * args.days
+        except Exception:
+            traffic = None
+    roofline = {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
+                "traffic": traffic, "peak_source": peak_src, "kernel": "k_run (persistent multi-day step)",
+                "algorithmic_bytes_per_point_day": B_FORCING + B_OUT, "launch_ms": launch_ms}
+    # second denominator: the path is FP64-pipe / issue bound for larger n_ksub -- measured DFMA peak
+    ms = C.c_float(0.0)
+    fl = C.c_double(0.0)
+    L.semic_probe_dfma(1 << 14, C.byref(ms), C.byref(fl))
+    check(L.semic_probe_dfma(1 << 16, C.byref(ms), C.byref(fl)))
+    dfma_tflops = fl.value / (ms.value * 1e-3) / 1e12
+    roofline["fp64_dfma_peak_tflops_measured"] = dfma_tflops
+
+    line = {"metric": "grid-point-days/s", "value": value, "unit": "point-days/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": kernel_ms / max(args.steps, 1), "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": workload_config(args, world), "roofline": roofline, "gpu_launches": launches,
+            "wall_ms_per_step": wall_ms / max(args.steps, 1), "clocks": clocks}
+    if e2e is not None:
+        line["e2e"] = e2e
+
+    if args.extra:
+        extra = {}
+        # C3 at n_ksub=24 on the same buffers
+        par24 = make_par(24, args.scheme)
+        engine.run(st, par24, bnd, forcing, 30, out=out, out_days=30, ppt=args.ppt)
+        t = engine.run(st, par24, bnd, forcing, args.days, out=out, out_days=args.days, ppt=args.ppt)
+        extra["C3_n_ksub24_point_days_per_s"] = float(N) * args.days / (t * 1e-3)
+        # C2: 100k points, 1 year, n_ksub=24, Greenland-like mask
+        st2 = make_state(100000, 0, 0.85, 0.10)
+        f2 = engine.Series(100000, 9, 365).synth_forcing(SEED)
+        o2 = engine.Series(100000, 8, 365)
+        for _ in range(3):
+            engine.run(st2, par24, bnd, f2, 365, out=o2, out_days=365)
+        ts = [engine.run(st2, par24, bnd, f2, 365, out=o2, out_days=365) for _ in range(5)]
+        extra["C2_100k_points_n_ksub24_point_days_per_s"] = 100000.0 * 365 / (min(ts) * 1e-3)
+        extra["C2_ms_per_year"] = min(ts)
+        par3 = make_par(3, args.scheme)
+        ts = [engine.run(st2, par3, bnd, f2, 365, out=o2, out_days=365) for _ in range(5)]
+        extra["C2_100k_points_n_ksub3_point_days_per_s"] = 100000.0 * 365 / (min(ts) * 1e-3)
+        line["extra"] = extra
+
+    if not args.no_cpu:
+        r, cores, sec = cpu_reference_rate(args.scheme, args.n_ksub, args.cpu_points_per_core, args.cpu_days, 2)
+        line["cpu_baseline"] = {"value": r, "unit": "point-days/s", "cores": cores, "kind": "port",
+                                "sample": "%d cores x %d points x %d days, best of 2 (array-form C oracle of surface_physics.f90, "
+                                          "gcc -O3 -fno-fast-math -ffp-contract=off; no Fortran compiler in the image)"
+                                          % (cores, args.cpu_points_per_core, args.cpu_days), "seconds": sec}
+    print(json.dumps(line))
+    if dist is not None:
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -137,8 +137,9 @@ int     semic_series_upload(semic_series *s, int day0, int ndays, const double *
 int     semic_series_download(const semic_series *s, int day0, int ndays, double *host, int host_ld,
                               int point0, int npoints);
 /* synthetic forcing of SURVEY.md 8(d) generated on the device (counter-based splitmix64): fills all
- * ndays x 9 rows for global points [point0, point0+npts), days [dayofs, dayofs+ndays). */
-int     semic_series_synth_forcing(semic_series *s, uint64_t seed, int64_t point0, int dayofs);
+ * ndays x 9 rows for global points [point0, point0+npts); row d holds calendar day dayofs + d*daystride
+ * (daystride > 1 samples the seasonal cycle into a short periodic window). */
+int     semic_series_synth_forcing(semic_series *s, uint64_t seed, int64_t point0, int dayofs, int daystride);
 /* synthetic mask: fractions of ice(2)/land(1), rest ocean(0); writes the host mirror AND the device */
 int     semic_state_synth_mask(semic_state *now, uint64_t seed, int64_t point0, double frac_ice, double frac_land);
 /* fill one field with a constant on host mirror and device (initial conditions) */

@@ -145,7 +145,7 @@ void oracle_energy_balance(oracle_state *now, const oracle_par *par, const oracl
     const int *mask = now->mask;
     double *qsb = (double *)malloc(sizeof(double) * (size_t)(nx > 0 ? nx : 1));    /* automatic array :167 */
 
-    if (now->branch) {
+    if (now->branch && !bnd->lhf) {
         /* flip report: the ts<t0 decision of latent_heat_flux (:415) is taken on tsurf BEFORE :199 */
         for (i = 0; i < nx; ++i) {
             if (tsurf[i] < t0) now->branch[i] |= OB_TS_LT_T0;

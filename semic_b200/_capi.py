@@ -95,7 +95,7 @@ PROTOTYPES = {
     "semic_series_device_ptr": (_vp, [_vp]),
     "semic_series_upload": (C.c_int, [_vp, C.c_int, C.c_int, _dp, C.c_int]),
     "semic_series_download": (C.c_int, [_vp, C.c_int, C.c_int, _dp, C.c_int, C.c_int, C.c_int]),
-    "semic_series_synth_forcing": (C.c_int, [_vp, C.c_uint64, C.c_int64, C.c_int]),
+    "semic_series_synth_forcing": (C.c_int, [_vp, C.c_uint64, C.c_int64, C.c_int, C.c_int]),
     "semic_state_synth_mask": (C.c_int, [_vp, C.c_uint64, C.c_int64, C.c_double, C.c_double]),
     "semic_state_fill": (C.c_int, [_vp, C.c_int, C.c_double]),
     "semic_run": (C.c_int, [_vp, C.POINTER(SemicPar), C.POINTER(SemicBnd), _vp, _vp, C.c_int, C.c_int, _vp,

@@ -179,7 +179,8 @@ __device__ __forceinline__ double gauss4(uint64_t seed, uint64_t point, uint32_t
 }
 
 // SURVEY.md 8(d) synthetic forcing; one thread per point, all days
-__global__ void k_synth_forcing(double *f, int npts, int ld, int ndays, uint64_t seed, long long point0, int dayofs)
+__global__ void k_synth_forcing(double *f, int npts, int ld, int ndays, uint64_t seed, long long point0, int dayofs,
+                                int daystride)
 {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= npts) return;
@@ -188,7 +189,7 @@ __global__ void k_synth_forcing(double *f, int npts, int ld, int ndays, uint64_t
     const double sp0 = 63000.0 + 37000.0 * uni(seed, pt, 0xFFFFFFFFu, 14, 0);
     const double t0 = 273.15, eps = 0.62197, pi = 3.141592653589793;
     for (int d = 0; d < ndays; ++d) {
-        const uint32_t day = (uint32_t)(dayofs + d);
+        const uint32_t day = (uint32_t)(dayofs + d * daystride);
         const int doy = (int)(day % 365u);
         const double t2m = tbar + 12.0 * cos(2.0 * pi * (doy - 200) / 365.0) + 3.0 * gauss4(seed, pt, day, SEMIC_V_T2M);
         double swd = 0.0;
@@ -584,12 +585,13 @@ extern "C" int semic_series_download(const semic_series *s, int day0, int ndays,
     return SEMIC_OK;
 }
 
-extern "C" int semic_series_synth_forcing(semic_series *s, uint64_t seed, int64_t point0, int dayofs)
+extern "C" int semic_series_synth_forcing(semic_series *s, uint64_t seed, int64_t point0, int dayofs, int daystride)
 {
     if (!s || s->nvar != SEMIC_NFORCING) { set_error("series_synth_forcing: series must have 9 variables"); return SEMIC_ERR_ARG; }
     CU(cudaSetDevice(s->device));
     if (s->npts > 0) {
-        k_synth_forcing<<<(s->npts + 127) / 128, 128>>>(s->d, s->npts, s->ld, s->ndays, seed, (long long)point0, dayofs);
+        k_synth_forcing<<<(s->npts + 127) / 128, 128>>>(s->d, s->npts, s->ld, s->ndays, seed, (long long)point0, dayofs,
+                                                        daystride > 0 ? daystride : 1);
         CU(cudaGetLastError());
         CU(cudaDeviceSynchronize());
     }
@@ -721,6 +723,7 @@ extern "C" int semic_run(semic_state *now, const semic_par *par, const semic_bnd
     int ppt = opts ? opts->ppt : 0;
     if (ppt != 1 && ppt != 2) ppt = 1;
     if (generic || strict) ppt = 1;
+    if (forcing->ld != now->ld || (vali && vali->ld != now->ld)) { set_error("semic_run: leading dimensions differ"); return SEMIC_ERR_ARG; }
     CU(cudaEventRecord(now->ev0, now->stream));
     cudaError_t e = strict ? launch_run_strict(a, generic, ppt, now->stream, &launches_total)
                            : launch_run_fast(a, generic, ppt, now->stream, &launches_total);

@@ -18,7 +18,7 @@ constexpr int kConsumerWarps = 8;
 constexpr int kConsumers     = kConsumerWarps * 32;      // 256
 constexpr int kThreads       = kConsumers + 32;          // 288
 constexpr int kStages        = 4;                        // days of forcing in flight per CTA
-constexpr int kLdAlign       = 1024;                     // leading dimensions are multiples of this (>= max tile)
+constexpr int kLdAlign       = 1024;                     // leading dimensions (even => 16-byte rows; the last tile may be ragged)
 constexpr int kForcingRows   = 9;
 constexpr int kExtRows       = 5;                        // tsurf alb smb melt acc overrides
 

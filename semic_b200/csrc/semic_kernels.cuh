@@ -72,6 +72,10 @@ __device__ __constant__ double kc[24] = {
     17.62, 243.12,                // 20 21  ew_sat a, b
     2.83e6, 2.5e6                 // 22 23  cls, clv
 };
+// dmax1/dmin1 as compare-select (3 instructions; IEEE fmax/fmin costs 6 on sm_100a, there is no DMNMX).
+// Identical to fmax/fmin on ordered operands; with a NaN operand the second argument is returned.
+DEVI double dmax1(double a, double b) { return a > b ? a : b; }
+DEVI double dmin1(double a, double b) { return a < b ? a : b; }
 #if SEMIC_STRICT
 DEVI double fdiv(double n, double d) { return n / d; }    // CUDA double division is IEEE round-to-nearest
 DEVI double fexp(double x) { return exp(x); }
@@ -82,10 +86,11 @@ DEVI double frcp(double d)
 {
     double r;
     asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(d));
-    double e = fma(-d, r, 1.0);
+    // two Newton steps; the second residual is e*e exactly (1 - d*r1 = e^2), which shortens the dependent chain
+    const double e = fma(-d, r, 1.0);
+    const double e2 = e * e;
     r = fma(r, e, r);
-    e = fma(-d, r, 1.0);
-    r = fma(r, e, r);
+    r = fma(r, e2, r);
     return r;
 }
 DEVI double fdiv(double n, double d) { return n * frcp(d); }
@@ -99,18 +104,21 @@ DEVI double fexp(double x)
     const double kf = t - magic;
     double r = fma(kf, kc[2], x);
     r = fma(kf, kc[3], r);
-    double p = kc[4];
-    p = fma(p, r, kc[5]);
-    p = fma(p, r, kc[6]);
-    p = fma(p, r, kc[7]);
-    p = fma(p, r, kc[8]);
-    p = fma(p, r, kc[9]);
-    p = fma(p, r, kc[10]);
-    p = fma(p, r, kc[11]);
-    p = fma(p, r, kc[12]);
-    p = fma(p, r, kc[13]);
-    p = fma(p, r, 1.0);
-    p = fma(p, r, 1.0);
+    // Estrin evaluation: dependent depth 5 instead of 11 (the sub-step loop is latency bound, not issue bound)
+    const double r2 = r * r;
+    const double p01 = r + 1.0;                       // c0 + c1 r          (c0 = c1 = 1)
+    const double p23 = fma(kc[12], r, kc[13]);        // c2 + c3 r
+    const double p45 = fma(kc[10], r, kc[11]);        // c4 + c5 r
+    const double p67 = fma(kc[8], r, kc[9]);          // c6 + c7 r
+    const double p89 = fma(kc[6], r, kc[7]);          // c8 + c9 r
+    const double pab = fma(kc[4], r, kc[5]);          // c10 + c11 r
+    const double r4 = r2 * r2;
+    const double q0 = fma(p23, r2, p01);              // c0..c3
+    const double q1 = fma(p67, r2, p45);              // c4..c7
+    const double q2 = fma(pab, r2, p89);              // c8..c11
+    const double r8 = r4 * r4;
+    const double h0 = fma(q1, r4, q0);                // c0..c7
+    double p = fma(q2, r8, h0);
     return __hiloint2double(__double2hiint(p) + (k << 20), __double2loint(p));
 }
 #endif
@@ -179,19 +187,19 @@ DEVI int diurnal_cycle(double amp, double tmean, double &above, double &below)
     above = tmean;
     below = 0.0;
     if (fabs(tmean) < amp) {                        // :465
-        // Reference operation order and IEEE division in BOTH arithmetic modes: for tmean -> -amp the
-        // numerator of `above` cancels to O(eps^1.5), so only the reference's own rounding sequence
-        // reproduces its digits.  The branch runs on the minority of days with a freeze/thaw cycle.
-        const double r = __ddiv_rn(tmean, amp);
+        // Reference operation order (unfused) in BOTH arithmetic modes: for tmean -> -amp the numerator of
+        // `above` cancels to O(eps^1.5), so only the reference's own rounding sequence comes close to its
+        // digits.  Divisions are IEEE in strict mode and ~1 ulp in fast mode.
+        const double r = fdiv(tmean, amp);
         double tmp1 = 0.0, tmp2 = 0.0;              // :452-453
         if (fabs(r) < 1.0) {                        // :454 (can differ from :465 only by the rounding of the quotient)
             tmp1 = acos(r);                         // :455
-            tmp2 = sqrt(__dsub_rn(1.0, __ddiv_rn(__dmul_rn(tmean, tmean), __dmul_rn(amp, amp))));      // :456
+            tmp2 = sqrt(__dsub_rn(1.0, fdiv(__dmul_rn(tmean, tmean), __dmul_rn(amp, amp))));           // :456
         }
         const double at2 = __dmul_rn(amp, tmp2);
-        above = __ddiv_rn(__dadd_rn(__dadd_rn(__dmul_rn(-tmean, tmp1), at2), __dmul_rn(c_pi, tmean)),
-                          __dsub_rn(c_pi, tmp1));                                                      // :467
-        below = __ddiv_rn(__dsub_rn(__dmul_rn(tmean, tmp1), at2), tmp1);                               // :469
+        above = fdiv(__dadd_rn(__dadd_rn(__dmul_rn(-tmean, tmp1), at2), __dmul_rn(c_pi, tmean)),
+                     __dsub_rn(c_pi, tmp1));                                                           // :467
+        below = fdiv(__dsub_rn(__dmul_rn(tmean, tmp1), at2), tmp1);                                    // :469
         return 1;
     }
     return 2;
@@ -234,9 +242,9 @@ DEVI double albedo_isba(double alb, double sf, double melt, const DevPar &P)
     double w_alb = 0.0;
     if (melt > 0.0) w_alb = fma(-melt, P.inv_mcrit, 1.0);
 #endif
-    w_alb = fmin(1.0, fmax(w_alb, 0.0));
+    w_alb = dmin1(1.0, dmax1(w_alb, 0.0));
     double a = (((1.0 - w_alb) * alb_dry) + (w_alb * alb_wet)) + alb_new;
-    return fmin(P.alb_smax, fmax(a, P.alb_smin));
+    return dmin1(P.alb_smax, dmax1(a, P.alb_smin));
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -257,14 +265,14 @@ struct Pt {
 // memory in k_ensemble): variable v is row[v*T].  Values are read where they are first needed (LDS
 // is cheap, registers across the sub-step loop are not); `swd_out` returns the day's shortwave for
 // the swnet diagnostic.
-template <int SCHEME, bool GENERIC>
+template <int SCHEME, bool GENERIC, bool WANT_BRANCH>
 DEVI unsigned point_day(Pt &s, const double *row, const long long T, const DevPar &P, const semic_bnd &B,
                         const int eb_steps, const int do_mb, double &swd_out)
 {
     unsigned branch = 0;
     const int mask = s.mask;
     const bool gate = (mask == 2) || (s.hsnow > 0.0);                 // :201,:209 (hsnow is constant over the sub-steps)
-    if (gate) branch |= SEMIC_B_GATE;
+    if (WANT_BRANCH) { if (gate) branch |= SEMIC_B_GATE; }
 
     double ts = s.tsurf;
     double t2m = row[SEMIC_V_T2M * T];
@@ -339,9 +347,9 @@ DEVI unsigned point_day(Pt &s, const double *row, const long long T, const DevPa
 #else
             qmr = over * P.ceff_over_sub;
 #endif
-            if (over > 0.0) branch |= SEMIC_B_CLAMP;
+            if (WANT_BRANCH) { if (over > 0.0) branch |= SEMIC_B_CLAMP; }
             if (!BND(lhf)) {
-                if (ice_last) branch |= SEMIC_B_TS_LT_T0;
+                if (WANT_BRANCH) { if (ice_last) branch |= SEMIC_B_TS_LT_T0; }
                 if (!GENERIC) {                                                    // :410-411,:420,:427 then :186
 #if SEMIC_STRICT
                     subl = ice_last ? fdiv(q_last, c_rhow) : 0.0;
@@ -369,17 +377,17 @@ DEVI unsigned point_day(Pt &s, const double *row, const long long T, const DevPa
 #endif
         double above, below;
         const int dbr = diurnal_cycle(amp, tmean, above, below);
-        branch |= (dbr == 1 ? SEMIC_B_DIURNAL_LO : (dbr == 2 ? SEMIC_B_DIURNAL_HI : 0));
+        if (WANT_BRANCH) { branch |= (dbr == 1 ? SEMIC_B_DIURNAL_LO : (dbr == 2 ? SEMIC_B_DIURNAL_HI : 0)); }
         qmr = 0.0;                                                                 // :250
 
         double qmelt = 0.0, qcold = 0.0;
         if (mask >= 1) {                                                           // :252-261
 #if SEMIC_STRICT
-            qmelt = fmax(0.0, fdiv(above * P.ceff, P.tstic));
-            qcold = fmax(0.0, fdiv(fabs(below) * P.ceff, P.tstic));
+            qmelt = dmax1(0.0, fdiv(above * P.ceff, P.tstic));
+            qcold = dmax1(0.0, fdiv(fabs(below) * P.ceff, P.tstic));
 #else
-            qmelt = fmax(0.0, above * P.ceff_over_tstic);
-            qcold = fmax(0.0, fabs(below) * P.ceff_over_tstic);
+            qmelt = dmax1(0.0, above * P.ceff_over_tstic);
+            qcold = dmax1(0.0, fabs(below) * P.ceff_over_tstic);
 #endif
         }
 #if SEMIC_STRICT
@@ -391,7 +399,7 @@ DEVI unsigned point_day(Pt &s, const double *row, const long long T, const DevPa
         // one-ulp ghost snow layer (which keeps the :201 gate on over land); keep the reference's rounding
         const double hs_rate = __ddiv_rn(hsnow, P.tstic);
 #endif
-        melted_snow = fmin(melt, hs_rate);                                         // :269
+        melted_snow = dmin1(melt, hs_rate);                                         // :269
         melted_ice  = melt - melted_snow;                                          // :270
         if (!BND(melt)) {                                                          // :272-280
             if (mask == 2) {
@@ -409,11 +417,11 @@ DEVI unsigned point_day(Pt &s, const double *row, const long long T, const DevPa
 #else
             refr = qcold * P.inv_rhow_clm;
 #endif
-            refrozen_rain = fmin(refr, rf);                                        // :287
-            refrozen_snow = fmax(refr - refrozen_rain, 0.0);                       // :289
-            refrozen_snow = fmin(refrozen_snow, melted_snow);                      // :291
-            refrozen_rain = P.rcrit * fmin(hs_rate, refrozen_rain);                // :293
-            refrozen_snow = P.rcrit * fmin(hs_rate, refrozen_snow);                // :294
+            refrozen_rain = dmin1(refr, rf);                                        // :287
+            refrozen_snow = dmax1(refr - refrozen_rain, 0.0);                       // :289
+            refrozen_snow = dmin1(refrozen_snow, melted_snow);                      // :291
+            refrozen_rain = P.rcrit * dmin1(hs_rate, refrozen_rain);                // :293
+            refrozen_snow = P.rcrit * dmin1(hs_rate, refrozen_snow);                // :294
             refr = refrozen_rain + refrozen_snow;                                  // :295
 #if SEMIC_STRICT
             qmr = qmr - (((P.one_m_frz * refr) * c_rhow) * 3.30e5);                // :298
@@ -428,11 +436,11 @@ DEVI unsigned point_day(Pt &s, const double *row, const long long T, const DevPa
 
         if (mask == 0) hsnow = 0.0;                                                // :315-320
 #if SEMIC_STRICT
-        else hsnow = fmax(0.0, hsnow + (smb_snow * P.tstic));
+        else hsnow = dmax1(0.0, hsnow + (smb_snow * P.tstic));
 #else
-        else hsnow = fmax(0.0, __dadd_rn(hsnow, __dmul_rn(smb_snow, P.tstic)));      // unfused, see hs_rate
+        else hsnow = dmax1(0.0, __dadd_rn(hsnow, __dmul_rn(smb_snow, P.tstic)));      // unfused, see hs_rate
 #endif
-        const double snow_to_ice = fmax(0.0, hsnow - c_hsmax);                     // :323
+        const double snow_to_ice = dmax1(0.0, hsnow - c_hsmax);                     // :323
         hsnow = hsnow - snow_to_ice;                                               // :324
 #if SEMIC_STRICT
         const double s2i_rate = fdiv(snow_to_ice, P.tstic);
@@ -445,11 +453,11 @@ DEVI unsigned point_day(Pt &s, const double *row, const long long T, const DevPa
 #endif
         if (!BND(smb)) {                                                           // :329-335
             if (mask == 2) smb = (smb_snow + smb_ice) - s2i_rate;
-            else           smb = smb_snow + fmax(0.0, smb_ice - s2i_rate);
+            else           smb = smb_snow + dmax1(0.0, smb_ice - s2i_rate);
         }
-        if (melt > 0.0) branch |= SEMIC_B_MELT_POS;
-        if (hsnow == 0.0) branch |= SEMIC_B_HSNOW_ZERO;
-        if (snow_to_ice > 0.0) branch |= SEMIC_B_SNOW2ICE;
+        if (WANT_BRANCH) { if (melt > 0.0) branch |= SEMIC_B_MELT_POS; }
+        if (WANT_BRANCH) { if (hsnow == 0.0) branch |= SEMIC_B_HSNOW_ZERO; }
+        if (WANT_BRANCH) { if (snow_to_ice > 0.0) branch |= SEMIC_B_SNOW2ICE; }
 
         if (!BND(alb)) {                                                           // :339 (Q6: the whole block is skipped)
 #if SEMIC_STRICT
@@ -485,47 +493,47 @@ DEVI unsigned point_day(Pt &s, const double *row, const long long T, const DevPa
 // ------------------------------------------------------------------------------------------------
 DEVI uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
-DEVI void mbar_init(uint64_t *bar, uint32_t count)
+DEVI void mbar_init(uint32_t bar, uint32_t count)
 {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
 }
 DEVI void mbar_fence_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
-DEVI void mbar_expect_tx(uint64_t *bar, uint32_t bytes)
+DEVI void mbar_expect_tx(uint32_t bar, uint32_t bytes)
 {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
 }
-DEVI void mbar_arrive(uint64_t *bar)
+DEVI void mbar_arrive(uint32_t bar)
 {
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
-DEVI void mbar_wait(uint64_t *bar, uint32_t parity)
+DEVI void mbar_wait(uint32_t bar, uint32_t parity)
 {
     asm volatile(
         "{\n"
         ".reg .pred p;\n"
         "WAIT_%=:\n"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, %2;\n"
         "@p bra DONE_%=;\n"
+        "nanosleep.u32 200;\n"
         "bra WAIT_%=;\n"
         "DONE_%=:\n"
-        "}\n" ::"r"(smem_u32(bar)), "r"(parity)
+        "}\n" ::"r"(bar), "r"(parity), "r"(0x989680u)   // suspend-time hint: sleep in hardware, do not spin
         : "memory");
 }
 // global -> shared bulk copy completing on an mbarrier (TMA unit, SASS UBLKCP); 16-byte aligned, size % 16 == 0
-DEVI void tma_load_1d(void *smem_dst, const void *gmem_src, uint32_t bytes, uint64_t *bar)
+DEVI void tma_load_1d(uint32_t smem_dst, const void *gmem_src, uint32_t bytes, uint32_t bar)
 {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
-                     smem_u32(smem_dst)),
-                 "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar))
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_dst),
+                 "l"(gmem_src), "r"(bytes), "r"(bar)
                  : "memory");
 }
 
 // ------------------------------------------------------------------------------------------------
 // the persistent multi-day kernel
 // ------------------------------------------------------------------------------------------------
-template <bool GENERIC, int PPT>
+template <bool GENERIC, int PPT, int CW>
 struct RunSmem {
-    static constexpr int T = kConsumers * PPT;
+    static constexpr int T = CW * 32 * PPT;
     static constexpr int ROWS = kForcingRows + (GENERIC ? kExtRows : 0);
     static constexpr int STAGES = (PPT == 1) ? kStages : 3;
     static constexpr size_t stage_bytes = (size_t)ROWS * T * sizeof(double);
@@ -535,24 +543,25 @@ struct RunSmem {
 // validation-layout rows that feed the overrides tsurf, alb, smb, melt, acc (example.f90:103-107)
 __device__ __constant__ int c_ext_var[kExtRows] = {SEMIC_O_STT, SEMIC_O_ALB, SEMIC_O_SMB, SEMIC_O_MELT, SEMIC_O_ACC};
 
-template <int SCHEME, bool GENERIC, int PPT, int MINB>
-__global__ void __launch_bounds__(kThreads, MINB) k_run(const __grid_constant__ RunArgs a)
+template <int SCHEME, bool GENERIC, int PPT, int MINB, bool BR, int CW>
+__global__ void __launch_bounds__(CW * 32 + 32, MINB) k_run(const __grid_constant__ RunArgs a)
 {
-    using SM = RunSmem<GENERIC, PPT>;
+    using SM = RunSmem<GENERIC, PPT, CW>;
     constexpr int T = SM::T;
     constexpr int ROWS = SM::ROWS;
     constexpr int NST = SM::STAGES;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     double *sbuf = reinterpret_cast<double *>(smem_raw);
-    uint64_t *full = reinterpret_cast<uint64_t *>(smem_raw + SM::stage_bytes * NST);
-    uint64_t *empty = full + NST;
+    const uint32_t sbuf_u32 = smem_u32(smem_raw);
+    const uint32_t full_u32 = sbuf_u32 + (uint32_t)(SM::stage_bytes * NST);     // full[s] at +8*s, empty[s] at +8*(NST+s)
+    const uint32_t empty_u32 = full_u32 + 8u * NST;
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
     if (threadIdx.x == 0) {
         for (int s = 0; s < NST; ++s) {
-            mbar_init(&full[s], 1);
-            mbar_init(&empty[s], kConsumerWarps);
+            mbar_init(full_u32 + 8u * s, 1);
+            mbar_init(empty_u32 + 8u * s, CW);
         }
         mbar_fence_init();
     }
@@ -565,31 +574,35 @@ __global__ void __launch_bounds__(kThreads, MINB) k_run(const __grid_constant__ 
         ext_on[3] = a.B.melt != 0;  ext_on[4] = a.B.acc != 0;
     }
 
-    if (warp == kConsumerWarps) {
+    if (warp == CW) {
         // ---------------- producer: one lane feeds the ring with TMA bulk copies ----------------
         if (lane == 0) {
-            uint32_t nbytes = kForcingRows * T * (uint32_t)sizeof(double);
-            if (GENERIC) for (int e = 0; e < kExtRows; ++e) if (ext_on[e]) nbytes += T * (uint32_t)sizeof(double);
+            int nrows = kForcingRows;
+            if (GENERIC) for (int e = 0; e < kExtRows; ++e) if (ext_on[e]) ++nrows;
             int stage = 0;
             uint32_t phase = 0;
             for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
                 const long long p0 = (long long)tile * T;
+                // ragged last tile: rows are ld long (ld is even, so the copy stays a multiple of 16 bytes)
+                const long long left = (long long)a.ld - p0;
+                const uint32_t rowb = (uint32_t)(left < T ? left : T) * (uint32_t)sizeof(double);
+                const uint32_t nbytes = rowb * (uint32_t)nrows;
                 int fd = a.f_day0 % a.f_nwin;
                 for (int d = 0; d < a.ndays; ++d) {
-                    mbar_wait(&empty[stage], phase ^ 1u);
-                    mbar_expect_tx(&full[stage], nbytes);
-                    double *dst = sbuf + (size_t)stage * ROWS * T;
+                    mbar_wait(empty_u32 + 8u * stage, phase ^ 1u);
+                    mbar_expect_tx(full_u32 + 8u * stage, nbytes);
+                    const uint32_t dst = sbuf_u32 + (uint32_t)stage * (uint32_t)SM::stage_bytes;
                     const double *src = a.forcing + (long long)fd * a.f_day_stride + p0;
 #pragma unroll
                     for (int v = 0; v < kForcingRows; ++v)
-                        tma_load_1d(dst + v * T, src + a.f_var_off[v], T * (uint32_t)sizeof(double), &full[stage]);
+                        tma_load_1d(dst + v * T * 8u, src + a.f_var_off[v], rowb, full_u32 + 8u * stage);
                     if (GENERIC) {
                         const double *vs = a.vali + (long long)fd * a.v_day_stride + p0;
 #pragma unroll
                         for (int e = 0; e < kExtRows; ++e)
                             if (ext_on[e])
-                                tma_load_1d(dst + (kForcingRows + e) * T, vs + c_ext_var[e] * a.v_var_stride,
-                                            T * (uint32_t)sizeof(double), &full[stage]);
+                                tma_load_1d(dst + (kForcingRows + e) * T * 8u, vs + c_ext_var[e] * a.v_var_stride, rowb,
+                                            full_u32 + 8u * stage);
                     }
                     if (++fd == a.f_nwin) fd = 0;
                     if (++stage == NST) { stage = 0; phase ^= 1u; }
@@ -600,7 +613,7 @@ __global__ void __launch_bounds__(kThreads, MINB) k_run(const __grid_constant__ 
     }
 
     // ---------------- consumers ----------------
-    const int tid = threadIdx.x;          // 0..255
+    const int tid = threadIdx.x;          // 0..CW*32-1
     const long long ld = a.ld;
     int stage = 0;
     uint32_t phase = 0;
@@ -646,13 +659,15 @@ __global__ void __launch_bounds__(kThreads, MINB) k_run(const __grid_constant__ 
             s[p].t2m = 0.0;
         }
 
+        // daily output: ring slot advances by one per written day (no modulo in the loop)
+        double *oday = (a.out != nullptr) ? a.out + i0 : nullptr;
+        int oslot = 0;
+        const long long ovs = a.o_var_stride;
+
         for (int d = 0; d < a.ndays; ++d) {
-            mbar_wait(&full[stage], phase);
+            mbar_wait(full_u32 + 8u * stage, phase);
             const double *row = sbuf + (size_t)stage * ROWS * T + tid * PPT;
-            const bool write_out = (a.out != nullptr) && (d >= a.out_start);
-            double *o = nullptr;
-            if (write_out) o = a.out + (long long)((d - a.out_start) % a.o_nring) * a.o_day_stride + i0;
-            double ov[SEMIC_NOUT + 1][PPT];
+            const bool write_out = (oday != nullptr) && (d >= a.out_start);
 #pragma unroll
             for (int p = 0; p < PPT; ++p) {
                 if (valid[p]) {
@@ -664,41 +679,28 @@ __global__ void __launch_bounds__(kThreads, MINB) k_run(const __grid_constant__ 
                         if (ext_on[4]) s[p].acc   = row[(kForcingRows + 4) * T + p];
                     }
                     double swd;
-                    const unsigned br = point_day<SCHEME, GENERIC>(s[p], row + p, T, a.P, a.B, a.eb_steps, a.do_mb, swd);
-                    ov[SEMIC_O_STT][p]   = s[p].tsurf;                 // example.f90:117-122
-                    ov[SEMIC_O_ALB][p]   = s[p].alb;
-                    ov[SEMIC_O_SWNET][p] = swd * (1.0 - s[p].alb);
-                    ov[SEMIC_O_SMB][p]   = s[p].smb;
-                    ov[SEMIC_O_MELT][p]  = s[p].melt;
-                    ov[SEMIC_O_ACC][p]   = s[p].acc;
-                    ov[SEMIC_O_SHF][p]   = s[p].shf;
-                    ov[SEMIC_O_LHF][p]   = s[p].lhf;
-                    ov[SEMIC_O_BRANCH][p] = (double)br;
-                } else {
-#pragma unroll
-                    for (int v = 0; v <= SEMIC_NOUT; ++v) ov[v][p] = 0.0;
+                    const unsigned br = point_day<SCHEME, GENERIC, BR>(s[p], row + p, T, a.P, a.B, a.eb_steps, a.do_mb, swd);
+                    if (write_out) {                                   // example.f90:117-122
+                        double *o = oday + p;
+                        o[0] = s[p].tsurf;                 o += ovs;   // SEMIC_O_STT
+                        o[0] = s[p].alb;                   o += ovs;   // SEMIC_O_ALB
+                        o[0] = swd * (1.0 - s[p].alb);     o += ovs;   // SEMIC_O_SWNET
+                        o[0] = s[p].smb;                   o += ovs;   // SEMIC_O_SMB
+                        o[0] = s[p].melt;                  o += ovs;   // SEMIC_O_MELT
+                        o[0] = s[p].acc;                   o += ovs;   // SEMIC_O_ACC
+                        o[0] = s[p].shf;                   o += ovs;   // SEMIC_O_SHF
+                        o[0] = s[p].lhf;                               // SEMIC_O_LHF
+                        if (BR) { o += ovs; o[0] = (double)br; }       // SEMIC_O_BRANCH (series with 9 rows)
+                    }
                 }
             }
             // every shared-memory read of this stage is done: hand it back to the producer
             __syncwarp();
-            if (lane == 0) mbar_arrive(&empty[stage]);
+            if (lane == 0) mbar_arrive(empty_u32 + 8u * stage);
             if (++stage == NST) { stage = 0; phase ^= 1u; }
-
             if (write_out) {
-                const int nv = a.o_nvar;
-                if (PPT == 2 && valid[PPT - 1]) {
-#pragma unroll
-                    for (int v = 0; v <= SEMIC_NOUT; ++v)
-                        if (v < nv) *reinterpret_cast<double2 *>(o + v * a.o_var_stride) = make_double2(ov[v][0], ov[v][PPT - 1]);
-                } else {
-#pragma unroll
-                    for (int p = 0; p < PPT; ++p)
-                        if (valid[p]) {
-#pragma unroll
-                            for (int v = 0; v <= SEMIC_NOUT; ++v)
-                                if (v < nv) o[v * a.o_var_stride + p] = ov[v][p];
-                        }
-                }
+                oday += a.o_day_stride;
+                if (++oslot == a.o_nring) { oslot = 0; oday -= (long long)a.o_nring * a.o_day_stride; }
             }
         }
 
@@ -790,7 +792,7 @@ __global__ void __launch_bounds__(32 * kEnsParticles) k_ensemble(const EnsArgs a
         for (int n = 0; n < a.ntime; ++n) {
             const double *row = a.forcing + (long long)n * a.f_day_stride + ii;
             double swd;
-            point_day<SCHEME_RUNTIME, false>(s, row, a.f_var_stride, P, B, P.n_ksub, 1, swd);
+            point_day<SCHEME_RUNTIME, false, false>(s, row, a.f_var_stride, P, B, P.n_ksub, 1, swd);
             if (lastloop) {                                              // run_particles.f90:148-157
                 const double *v = a.vali + (long long)n * a.v_day_stride + ii;
                 double d[4];
@@ -813,7 +815,7 @@ __global__ void __launch_bounds__(32 * kEnsParticles) k_ensemble(const EnsArgs a
     const double n = (double)a.ntime;
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
-        const double var_d = fmax(0.0, (see[q] - se[q] * se[q] / n) / n);
+        const double var_d = dmax1(0.0, (see[q] - se[q] * se[q] / n) / n);
         c += var_d * a.inv_var[(long long)q * ld + ii];
     }
     if (!valid) c = 0.0;

@@ -39,16 +39,19 @@ cudaError_t launch_run_fast(const RunArgs &a, bool generic, int ppt, cudaStream_
     if (launches) ++*launches;
     if (generic) return fast_mode::launch_scheme<true, 1, 1>(a, st);
     // tuning knob: resident CTAs per SM the kernel is compiled for (register budget 65536/(288*MINB))
-    static int minb = -1;
-    if (minb < 0) {
-        const char *e = getenv("SEMIC_MINB");
-        minb = e ? atoi(e) : 2;
-        if (minb < 1 || minb > 3) minb = 2;
-    }
+    const char *e = getenv("SEMIC_MINB");
+    int minb = e ? atoi(e) : 2;
+    if (minb < 1 || minb > 3) minb = 2;
     if (ppt == 2) {
-        if (minb >= 2) return fast_mode::launch_scheme<false, 2, 2>(a, st);
-        return fast_mode::launch_scheme<false, 2, 1>(a, st);
+        const char *c2 = getenv("SEMIC_CW");
+        if (c2 && atoi(c2) == 7) return fast_mode::launch_scheme<false, 2, 2, 7>(a, st);
+        return fast_mode::launch_scheme<false, 2, 1, 15>(a, st);
     }
+    const char *c = getenv("SEMIC_CW");
+    const int cw = c ? atoi(c) : 20;      // default: one CTA of 20 consumer warps + 1 producer per SM (profiles/r01_tuning.md)
+    if (cw == 20) return fast_mode::launch_scheme<false, 1, 1, 20>(a, st);
+    if (cw == 10) return fast_mode::launch_scheme<false, 1, 2, 10>(a, st);
+    if (cw == 6) return fast_mode::launch_scheme<false, 1, 3, 6>(a, st);
     if (minb == 1) return fast_mode::launch_scheme<false, 1, 1>(a, st);
     if (minb == 3) return fast_mode::launch_scheme<false, 1, 3>(a, st);
     return fast_mode::launch_scheme<false, 1, 2>(a, st);

@@ -39,8 +39,8 @@ class Series(object):
                                           int(npoints), int(point0), int(npoints)))
         return out
 
-    def synth_forcing(self, seed, point0=0, dayofs=0):
-        check(lib().semic_series_synth_forcing(self._h, int(seed), int(point0), int(dayofs)))
+    def synth_forcing(self, seed, point0=0, dayofs=0, daystride=1):
+        check(lib().semic_series_synth_forcing(self._h, int(seed), int(point0), int(dayofs), int(daystride)))
         return self
 
     def free(self):
