@@ -415,3 +415,52 @@ def test_large_grid_properties():
     fin_s, out_s, _ = run_shard(p0, n)
     assert np.array_equal(fin_s[:23], fin[:23, p0:p0 + n])
     assert np.array_equal(out_s, out[:, :, p0:p0 + n])
+
+
+# ------------------------------------------------------------------------------------------------------------
+# ensemble misfit (config 5): optimize/run_particles.f90 + utils.calculate_crmsd, one all-reduce
+# ------------------------------------------------------------------------------------------------------------
+def _ensemble_case(nx, ntime, mask):
+    from semic_b200 import synth
+    forc = synth.forcing(nx, ntime, daystride=3)
+    r = np.random.default_rng(0)
+    vali = np.ascontiguousarray(r.normal(size=(ntime, 8, nx)) * np.array([5, .1, 30, 1e-8, 1e-8, 1e-8, 5, 5])[None, :, None]
+                                + np.array([260, .7, 60, 0, 1e-8, 1e-8, 0, 0])[None, :, None])
+    names = ["hcrit", "alb_smax", "amp", "rcrit", "albi", "albl"]                 # optimize/namelist.ranges
+    lo = np.array([0.01, 0.80, 0.5, 0.0, 0.35, 0.05])
+    hi = np.array([0.5, 0.9, 5.0, 1.0, 0.55, 0.40])
+    pop = [{"id": i, "pos": list(lo + (hi - lo) * r.uniform(size=6))} for i in range(13)]
+    init = dict(hsnow=1.0, hice=0.0, alb=0.8, tsurf=260.0, alb_snow=0.8)
+    return forc, vali, names, pop, init
+
+
+def test_ensemble_cost_matches_oracle():
+    from semic_b200 import driver
+    from tests.test_dist_gloo import _oracle_partials
+    nx, ntime, nloop = 333, 90, 2
+    mask = np.full(nx, 2, dtype=np.int32)
+    mask[::9] = 0
+    forc, vali, names, pop, init = _ensemble_case(nx, ntime, mask)
+    cost_gpu = driver.run_particles(pop, names, forc, vali, mask, init, ntime, nloop)
+    cost_ref = driver.run_particles(pop, names, forc, vali, mask, init, ntime, nloop, partial_fn=_oracle_partials)
+    err = max(abs(cost_gpu[k] - cost_ref[k]) / cost_ref[k] for k in cost_ref)
+    print("\n[ensemble] 13 particles x %d points x %d days x %d loops: max rel cost error %.3e" % (nx, ntime, nloop, err))
+    assert err <= 1e-9          # one-pass shifted sums on the device vs the reference's two-pass CRMSD
+
+
+def test_ensemble_with_nccl_communicator_single_rank():
+    """the library's own NCCL plumbing (unique id -> comm init -> in-place all-reduce) on a 1-rank communicator"""
+    import ctypes as C
+    from semic_b200 import driver
+    from semic_b200._capi import check, lib
+    nx, ntime, nloop = 200, 40, 1
+    mask = np.full(nx, 2, dtype=np.int32)
+    forc, vali, names, pop, init = _ensemble_case(nx, ntime, mask)
+    uid = C.create_string_buffer(128)
+    check(lib().semic_comm_unique_id(uid))
+    comm = C.c_void_p()
+    check(lib().semic_comm_init(C.byref(comm), uid, 1, 0))
+    a = driver.run_particles(pop, names, forc, vali, mask, init, ntime, nloop, comm=comm)
+    b = driver.run_particles(pop, names, forc, vali, mask, init, ntime, nloop)
+    check(lib().semic_comm_free(comm))
+    assert a == b
