@@ -76,6 +76,28 @@ __device__ __constant__ double kc[24] = {
 // Identical to fmax/fmin on ordered operands; with a NaN operand the second argument is returned.
 DEVI double dmax1(double a, double b) { return a > b ? a : b; }
 DEVI double dmin1(double a, double b) { return a < b ? a : b; }
+// 2^(j/64), j = 0..63 (correctly rounded), staged into shared memory by the kernels that use fexp_t
+__device__ __constant__ double c_exp2_tab[64] = {
+    1, 1.0108892860517005, 1.0218971486541166, 1.0330248790212284,
+    1.0442737824274138, 1.0556451783605572, 1.0671404006768237, 1.0787607977571199,
+    1.0905077326652577, 1.1023825833078409, 1.1143867425958924, 1.1265216186082418,
+    1.1387886347566916, 1.1511892299529827, 1.1637248587775775, 1.1763969916502812,
+    1.189207115002721, 1.2021567314527031, 1.215247359980469, 1.22848053610687,
+    1.241857812073484, 1.2553807570246911, 1.2690509571917332, 1.2828700160787783,
+    1.2968395546510096, 1.3109612115247644, 1.3252366431597413, 1.3396675240533029,
+    1.3542555469368927, 1.3690024229745905, 1.383909881963832, 1.3989796725383112,
+    1.4142135623730951, 1.42961333839197, 1.4451808069770467, 1.460917794180647,
+    1.4768261459394993, 1.4929077282912648, 1.5091644275934228, 1.5255981507445384,
+    1.5422108254079407, 1.5590044002378369, 1.5759808451078865, 1.593142151342267,
+    1.6104903319492543, 1.6280274218573478, 1.6457554781539649, 1.6636765803267364,
+    1.681792830507429, 1.7001063537185235, 1.7186192981224779, 1.7373338352737062,
+    1.7562521603732995, 1.7753764925265212, 1.7947090750031072, 1.8142521755003989,
+    1.8340080864093424, 1.8539791250833855, 1.8741676341103, 1.8945759815869656,
+    1.9152065613971474, 1.9360617934922943, 1.9571441241754002, 1.9784560263879509
+};
+// constants of the table-driven exp: 64/ln2, 1.5*2^52, -(ln2/64) hi (low 20 mantissa bits zero) and lo, Taylor 1/2..1/120
+__device__ __constant__ double kt[8] = {92.33248261689366, 6755399441055744.0, -0.010830424695086549, -1.162596423439437e-12,
+                                        0.5, 1.6666666666666666e-01, 4.1666666666666664e-02, 8.3333333333333332e-03};
 #if SEMIC_STRICT
 DEVI double fdiv(double n, double d) { return n / d; }    // CUDA double division is IEEE round-to-nearest
 DEVI double fexp(double x) { return exp(x); }
@@ -121,6 +143,24 @@ DEVI double fexp(double x)
     double p = fma(q2, r8, h0);
     return __hiloint2double(__double2hiint(p) + (k << 20), __double2loint(p));
 }
+// Table-driven exp for the hot loop: exp(x) = 2^k * 2^(j/64) * p(r), n = rint(x*64/ln2) = 64k + j,
+// |r| <= ln2/128, p = degree-5 Taylor (truncation 3.4e-17).  11 FP64 operations instead of 20 and 8 constants
+// instead of 14; the table lives in shared memory (LDS with a lane-varying index).  |x| < 700, no specials.
+DEVI double fexp_t(double x, const double *tab)
+{
+    const double t = fma(x, kt[0], kt[1]);
+    const int n = __double2loint(t);
+    const double nf = t - kt[1];
+    double r = fma(nf, kt[2], x);
+    r = fma(nf, kt[3], r);
+    const double r2 = r * r;
+    const double p01 = r + 1.0;
+    const double p23 = fma(kt[5], r, kt[4]);
+    const double p45 = fma(kt[7], r, kt[6]);
+    const double q = fma(p45, r2, p23);
+    const double p = fma(q, r2, p01) * tab[n & 63];
+    return __hiloint2double(__double2hiint(p) + ((n >> 6) << 20), __double2loint(p));
+}
 #endif
 
 // ------------------------------------------------------------------------------------------------
@@ -149,8 +189,9 @@ DEVI double esat(double ts, bool ice)
 }
 
 // latent_heat_flux, surface_physics.f90:393-430; returns q = subl (ice) or evap (water) in kg/(s m2)
-DEVI double latent_q(double ts, double wind_clh_rho, double shum, double sp, bool ice)
+DEVI double latent_q(double ts, double wind_clh_rho, double shum, double sp, bool ice, const double *tab)
 {
+    (void)tab;
 #if SEMIC_STRICT
     const double es = esat(ts, ice);
     const double shum_sat = fdiv(es * c_eps, (es * (c_eps - 1.0)) + sp);
@@ -159,7 +200,7 @@ DEVI double latent_q(double ts, double wind_clh_rho, double shum, double sp, boo
     const double a = ice ? kc[18] : kc[20];
     const double b = ice ? kc[19] : kc[21];
     const double x = ts - kc[14];
-    const double e = fexp((a * x) * frcp(b + x));
+    const double e = fexp_t((a * x) * frcp(b + x), tab);
     const double shum_sat = (e * kc[15]) * frcp(fma(e, kc[16], sp));
 #endif
     return wind_clh_rho * (shum_sat - shum);
@@ -224,7 +265,7 @@ DEVI double albedo_denby(double melt, const DevPar &P)
 #if SEMIC_STRICT
     return P.alb_smin + (P.smax_m_smin * fexp(fdiv(-melt, P.mcrit)));
 #else
-    return fma(P.smax_m_smin, fexp(-melt * P.inv_mcrit), P.alb_smin);
+    return fma(P.smax_m_smin, fexp(dmin1(700.0, dmax1(-700.0, -melt * P.inv_mcrit))), P.alb_smin);
 #endif
 }
 
@@ -267,7 +308,7 @@ struct Pt {
 // the swnet diagnostic.
 template <int SCHEME, bool GENERIC, bool WANT_BRANCH>
 DEVI unsigned point_day(Pt &s, const double *row, const long long T, const DevPar &P, const semic_bnd &B,
-                        const int eb_steps, const int do_mb, double &swd_out)
+                        const int eb_steps, const int do_mb, double &swd_out, const double *tab)
 {
     unsigned branch = 0;
     const int mask = s.mask;
@@ -298,11 +339,11 @@ DEVI unsigned point_day(Pt &s, const double *row, const long long T, const DevPa
             if (!BND(lhf)) {                                                       // :179-185
 #if SEMIC_STRICT
                 const bool ice = ts < c_t0;                                        // :415
-                const double q = latent_q(ts, lhf_c, qq, sp, ice);
+                const double q = latent_q(ts, lhf_c, qq, sp, ice, tab);
                 lhf = q * (ice ? c_cls : c_clv);                                   // :421,:428
 #else
                 const bool ice = ts < kc[14];
-                const double q = latent_q(ts, lhf_c, qq, sp, ice);
+                const double q = latent_q(ts, lhf_c, qq, sp, ice, tab);
                 lhf = q * (ice ? kc[22] : kc[23]);
 #endif
                 q_last = q;
@@ -463,7 +504,8 @@ DEVI unsigned point_day(Pt &s, const double *row, const long long T, const DevPa
 #if SEMIC_STRICT
             const double f_alb = 1.0 - fexp(fdiv(-hsnow, P.hcrit_eps));            // :338
 #else
-            const double f_alb = 1.0 - fexp(-hsnow * P.inv_hcrit_eps);
+            // hcrit -> 0 makes the argument huge: exp(-700) is already 0 next to 1
+            const double f_alb = 1.0 - fexp_t(dmax1(-700.0, -hsnow * P.inv_hcrit_eps), tab);
 #endif
             const int scheme = (SCHEME == SCHEME_RUNTIME) ? P.scheme : SCHEME;
             if (scheme == SCHEME_SLATER)      alb_snow = albedo_slater(ts, P);     // :340-341
@@ -514,7 +556,7 @@ DEVI void mbar_wait(uint32_t bar, uint32_t parity)
         "WAIT_%=:\n"
         "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, %2;\n"
         "@p bra DONE_%=;\n"
-        "nanosleep.u32 200;\n"
+        "nanosleep.u32 800;\n"
         "bra WAIT_%=;\n"
         "DONE_%=:\n"
         "}\n" ::"r"(bar), "r"(parity), "r"(0x989680u)   // suspend-time hint: sleep in hardware, do not spin
@@ -537,7 +579,8 @@ struct RunSmem {
     static constexpr int ROWS = kForcingRows + (GENERIC ? kExtRows : 0);
     static constexpr int STAGES = (PPT == 1) ? kStages : 3;
     static constexpr size_t stage_bytes = (size_t)ROWS * T * sizeof(double);
-    static constexpr size_t bytes = stage_bytes * STAGES + 2 * STAGES * sizeof(uint64_t);
+    static constexpr size_t bar_bytes = 2 * STAGES * sizeof(uint64_t);
+    static constexpr size_t bytes = stage_bytes * STAGES + bar_bytes + 64 * sizeof(double);      // ring, barriers, exp table
 };
 
 // validation-layout rows that feed the overrides tsurf, alb, smb, melt, acc (example.f90:103-107)
@@ -556,6 +599,8 @@ __global__ void __launch_bounds__(CW * 32 + 32, MINB) k_run(const __grid_constan
     const uint32_t full_u32 = sbuf_u32 + (uint32_t)(SM::stage_bytes * NST);     // full[s] at +8*s, empty[s] at +8*(NST+s)
     const uint32_t empty_u32 = full_u32 + 8u * NST;
 
+    double *tab = reinterpret_cast<double *>(smem_raw + SM::stage_bytes * NST + SM::bar_bytes);
+
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
     if (threadIdx.x == 0) {
@@ -565,6 +610,7 @@ __global__ void __launch_bounds__(CW * 32 + 32, MINB) k_run(const __grid_constan
         }
         mbar_fence_init();
     }
+    if (threadIdx.x < 64) tab[threadIdx.x] = c_exp2_tab[threadIdx.x];
     __syncthreads();
 
     const int ntiles = (a.nx + T - 1) / T;
@@ -679,7 +725,7 @@ __global__ void __launch_bounds__(CW * 32 + 32, MINB) k_run(const __grid_constan
                         if (ext_on[4]) s[p].acc   = row[(kForcingRows + 4) * T + p];
                     }
                     double swd;
-                    const unsigned br = point_day<SCHEME, GENERIC, BR>(s[p], row + p, T, a.P, a.B, a.eb_steps, a.do_mb, swd);
+                    const unsigned br = point_day<SCHEME, GENERIC, BR>(s[p], row + p, T, a.P, a.B, a.eb_steps, a.do_mb, swd, SEMIC_STRICT ? nullptr : tab);
                     if (write_out) {                                   // example.f90:117-122
                         double *o = oday + p;
                         o[0] = s[p].tsurf;                 o += ovs;   // SEMIC_O_STT
@@ -753,6 +799,8 @@ constexpr int kEnsParticles = 8;
 __global__ void __launch_bounds__(32 * kEnsParticles) k_ensemble(const EnsArgs a, const int ngroups)
 {
     __shared__ DevPar s_par[kEnsParticles];
+    __shared__ double tab[64];
+    if (threadIdx.x < 64) tab[threadIdx.x] = c_exp2_tab[threadIdx.x];
     const int tile = blockIdx.x / ngroups;
     const int group = blockIdx.x % ngroups;
     const int lane = threadIdx.x & 31;
@@ -792,7 +840,7 @@ __global__ void __launch_bounds__(32 * kEnsParticles) k_ensemble(const EnsArgs a
         for (int n = 0; n < a.ntime; ++n) {
             const double *row = a.forcing + (long long)n * a.f_day_stride + ii;
             double swd;
-            point_day<SCHEME_RUNTIME, false, false>(s, row, a.f_var_stride, P, B, P.n_ksub, 1, swd);
+            point_day<SCHEME_RUNTIME, false, false>(s, row, a.f_var_stride, P, B, P.n_ksub, 1, swd, tab);
             if (lastloop) {                                              // run_particles.f90:148-157
                 const double *v = a.vali + (long long)n * a.v_day_stride + ii;
                 double d[4];
