@@ -74,7 +74,8 @@ typedef struct semic_bnd {
 } semic_bnd;
 
 typedef struct semic_state  semic_state;    /* surface_state_class: device SoA + pinned host mirror */
-typedef struct semic_series semic_series;   /* device-resident [day][var][point] time series          */
+typedef struct semic_series semic_series;   /* device-resident time series, logically [day][var][point]; stored
+                                               tile-interleaved in HBM ([day][point/32][var][32]), see DESIGN.md */
 typedef struct semic_comm   semic_comm;     /* NCCL communicator wrapper (ensemble all-reduce)        */
 
 /* ---- module procedures (same order as surface_physics.f90:121-130) ------------------------- */
@@ -149,7 +150,7 @@ int     semic_state_fill(semic_state *now, int field, double value);
 typedef struct semic_run_opts {
     int strict;        /* 0 = fast math (default), 1 = reference operation order, IEEE div, no FMA contraction */
     int out_days;      /* write daily output for the LAST out_days days of the run (0 = none)       */
-    int ppt;           /* points per thread: 0 = library default, 1 or 2                              */
+    int ppt;           /* reserved (points per thread; one point per thread measured fastest)         */
     int reserved[5];
 } semic_run_opts;
 

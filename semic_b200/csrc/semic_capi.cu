@@ -208,16 +208,17 @@ __global__ void k_synth_forcing(double *f, int npts, int ld, int ndays, uint64_t
             sf = -3.5e-8 * log(1.0 - uni(seed, pt, day, SEMIC_V_SF, 1));
         if (t2m > 268.0 && uni(seed, pt, day, SEMIC_V_RF, 0) >= 0.6)
             rf = -6.0e-9 * log(1.0 - uni(seed, pt, day, SEMIC_V_RF, 1));
-        double *row = f + (size_t)d * SEMIC_NFORCING * (size_t)ld + i;
-        row[(size_t)SEMIC_V_SF * ld] = sf;
-        row[(size_t)SEMIC_V_RF * ld] = rf;
-        row[(size_t)SEMIC_V_SWD * ld] = swd;
-        row[(size_t)SEMIC_V_LWD * ld] = lwd;
-        row[(size_t)SEMIC_V_WIND * ld] = wind;
-        row[(size_t)SEMIC_V_SP * ld] = sp;
-        row[(size_t)SEMIC_V_RHOA * ld] = rhoa;
-        row[(size_t)SEMIC_V_QQ * ld] = qq;
-        row[(size_t)SEMIC_V_T2M * ld] = t2m;
+        // tiled series layout: ((day*ntl + tile)*nvar + var)*32 + lane
+        double *row = f + (((size_t)d * (size_t)(ld / kTile) + (size_t)(i / kTile)) * SEMIC_NFORCING) * kTile + (i % kTile);
+        row[SEMIC_V_SF * kTile] = sf;
+        row[SEMIC_V_RF * kTile] = rf;
+        row[SEMIC_V_SWD * kTile] = swd;
+        row[SEMIC_V_LWD * kTile] = lwd;
+        row[SEMIC_V_WIND * kTile] = wind;
+        row[SEMIC_V_SP * kTile] = sp;
+        row[SEMIC_V_RHOA * kTile] = rhoa;
+        row[SEMIC_V_QQ * kTile] = qq;
+        row[SEMIC_V_T2M * kTile] = t2m;
     }
 }
 
@@ -233,6 +234,39 @@ __global__ void k_fill(double *p, int n, double v)
 {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) p[i] = v;
+}
+
+// SoA rows [nd][nvar][ld_soa] (points [p0, p0+np) of the series) <-> tiled series [..][ld/32][nvar][32]
+__global__ void k_soa_to_tiled(const double *soa, long long ld_soa, double *tiled, int ld, int nvar, int day0, int nd, int np)
+{
+    const long long n = (long long)nd * nvar * np;
+    for (long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x; k < n; k += (long long)gridDim.x * blockDim.x) {
+        const int i = (int)(k % np);
+        const int v = (int)((k / np) % nvar);
+        const int d = (int)(k / ((long long)np * nvar));
+        tiled[(((long long)(day0 + d) * (ld / kTile) + i / kTile) * nvar + v) * kTile + (i % kTile)] =
+            soa[((long long)d * nvar + v) * ld_soa + i];
+    }
+}
+__global__ void k_tiled_to_soa(const double *tiled, int ld, int nvar, int day0, int nd, int p0, int np, double *soa,
+                               long long ld_soa)
+{
+    const long long n = (long long)nd * nvar * np;
+    for (long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x; k < n; k += (long long)gridDim.x * blockDim.x) {
+        const int j = (int)(k % np);
+        const int v = (int)((k / np) % nvar);
+        const int d = (int)(k / ((long long)np * nvar));
+        const int i = p0 + j;
+        soa[((long long)d * nvar + v) * ld_soa + j] =
+            tiled[(((long long)(day0 + d) * (ld / kTile) + i / kTile) * nvar + v) * kTile + (i % kTile)];
+    }
+}
+
+// one variable of one day of a tiled series -> a contiguous row
+__global__ void k_tiled_var_to_row(const double *tiled, int ld, int nvar, int day, int var, int np, double *dst)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < np) dst[i] = tiled[(((long long)day * (ld / kTile) + i / kTile) * nvar + var) * kTile + (i % kTile)];
 }
 
 // field_average, surface_physics.f90:601-629, over the 19 averaged fields (:574-593)
@@ -558,6 +592,16 @@ extern "C" int semic_series_nvar(const semic_series *s) { return s ? s->nvar : S
 extern "C" int semic_series_ndays(const semic_series *s) { return s ? s->ndays : SEMIC_ERR_ARG; }
 extern "C" double *semic_series_device_ptr(semic_series *s) { return s ? s->d : nullptr; }
 
+// Host arrays are SoA per day ([ndays][nvar][host_ld], the layout of the reference's files and arrays); the device
+// series is tile-interleaved, so transfers go through a bounded SoA staging buffer and a transpose kernel.
+static int staging_days(int ndays, int nvar, int np)
+{
+    const size_t per_day = (size_t)nvar * (size_t)np * sizeof(double);
+    size_t cap = (256ull << 20) / (per_day ? per_day : 1);
+    if (cap < 1) cap = 1;
+    return (size_t)ndays < cap ? ndays : (int)cap;
+}
+
 extern "C" int semic_series_upload(semic_series *s, int day0, int ndays, const double *host, int host_ld)
 {
     if (!s || !host || day0 < 0 || ndays < 0 || day0 + ndays > s->ndays || host_ld < s->npts) {
@@ -566,9 +610,23 @@ extern "C" int semic_series_upload(semic_series *s, int day0, int ndays, const d
     }
     CU(cudaSetDevice(s->device));
     if (ndays == 0 || s->npts == 0) return SEMIC_OK;
-    CU(cudaMemcpy2D(s->d + (size_t)day0 * s->nvar * s->ld, (size_t)s->ld * 8, host, (size_t)host_ld * 8,
-                    (size_t)s->npts * 8, (size_t)ndays * s->nvar, cudaMemcpyHostToDevice));
-    return SEMIC_OK;
+    const int chunk = staging_days(ndays, s->nvar, s->npts);
+    double *tmp = nullptr;
+    CU(cudaMalloc(&tmp, (size_t)chunk * s->nvar * s->npts * sizeof(double)));
+    int rc = SEMIC_OK;
+    for (int d = 0; d < ndays && rc == SEMIC_OK; d += chunk) {
+        const int nd = ndays - d < chunk ? ndays - d : chunk;
+        cudaError_t e = cudaMemcpy2D(tmp, (size_t)s->npts * 8, host + (size_t)d * s->nvar * host_ld, (size_t)host_ld * 8,
+                                     (size_t)s->npts * 8, (size_t)nd * s->nvar, cudaMemcpyHostToDevice);
+        if (e == cudaSuccess) {
+            k_soa_to_tiled<<<1184, 256>>>(tmp, s->npts, s->d, s->ld, s->nvar, day0 + d, nd, s->npts);
+            e = cudaGetLastError();
+        }
+        if (e == cudaSuccess) e = cudaDeviceSynchronize();
+        if (e != cudaSuccess) rc = cuda_fail(e, "series_upload");
+    }
+    cudaFree(tmp);
+    return rc;
 }
 extern "C" int semic_series_download(const semic_series *s, int day0, int ndays, double *host, int host_ld, int point0,
                                      int npoints)
@@ -580,9 +638,21 @@ extern "C" int semic_series_download(const semic_series *s, int day0, int ndays,
     }
     CU(cudaSetDevice(s->device));
     if (ndays == 0 || npoints == 0) return SEMIC_OK;
-    CU(cudaMemcpy2D(host, (size_t)host_ld * 8, s->d + (size_t)day0 * s->nvar * s->ld + point0, (size_t)s->ld * 8,
-                    (size_t)npoints * 8, (size_t)ndays * s->nvar, cudaMemcpyDeviceToHost));
-    return SEMIC_OK;
+    const int chunk = staging_days(ndays, s->nvar, npoints);
+    double *tmp = nullptr;
+    CU(cudaMalloc(&tmp, (size_t)chunk * s->nvar * npoints * sizeof(double)));
+    int rc = SEMIC_OK;
+    for (int d = 0; d < ndays && rc == SEMIC_OK; d += chunk) {
+        const int nd = ndays - d < chunk ? ndays - d : chunk;
+        k_tiled_to_soa<<<1184, 256>>>(s->d, s->ld, s->nvar, day0 + d, nd, point0, npoints, tmp, npoints);
+        cudaError_t e = cudaGetLastError();
+        if (e == cudaSuccess)
+            e = cudaMemcpy2D(host + (size_t)d * s->nvar * host_ld, (size_t)host_ld * 8, tmp, (size_t)npoints * 8,
+                             (size_t)npoints * 8, (size_t)nd * s->nvar, cudaMemcpyDeviceToHost);
+        if (e != cudaSuccess) rc = cuda_fail(e, "series_download");
+    }
+    cudaFree(tmp);
+    return rc;
 }
 
 extern "C" int semic_series_synth_forcing(semic_series *s, uint64_t seed, int64_t point0, int dayofs, int daystride)
@@ -610,7 +680,7 @@ static int check_par(const semic_par *par, const char *who)
     return SEMIC_OK;
 }
 
-// one fused launch on the state's own slab (forcing = the state's forcing fields)
+// one fused launch on the state's own slab (forcing = the state's SoA forcing fields)
 static int step_on_slab(semic_state *s, const semic_par *par, const semic_bnd *bnd, int eb_steps, int do_mb, bool whole_step,
                         int strict)
 {
@@ -618,18 +688,18 @@ static int step_on_slab(semic_state *s, const semic_par *par, const semic_bnd *b
     std::memset(&a, 0, sizeof a);
     a.slab = s->d_slab; a.mask = s->d_mask; a.nx = s->npts; a.ld = s->ld;
     a.forcing = s->d_slab;
-    a.f_day_stride = 0; a.f_nwin = 1; a.f_day0 = 0;
+    a.f_tiled = 0; a.f_nwin = 1; a.f_day0 = 0;
     const int src_field[kForcingRows] = {SEMIC_F_SF, SEMIC_F_RF, SEMIC_F_SWD, SEMIC_F_LWD, SEMIC_F_WIND, SEMIC_F_SP,
                                          SEMIC_F_RHOA, SEMIC_F_QQ, SEMIC_F_T2M};
     for (int v = 0; v < kForcingRows; ++v) a.f_var_off[v] = (long long)src_field[v] * s->ld;
-    a.vali = nullptr; a.out = nullptr; a.o_nring = 1; a.o_nvar = 0; a.out_start = 0;
+    a.vali = nullptr; a.out = nullptr; a.o_nring = 1; a.o_nvar = SEMIC_NOUT; a.out_start = 0;
     a.ndays = 1;
-    a.eb_steps = eb_steps; a.do_mb = do_mb; a.write_forcing_back = 0;
+    a.eb_steps = eb_steps; a.do_mb = do_mb;
     a.P = make_devpar(par);
     a.B = *bnd;
     const bool generic = !whole_step || any_consulted_flag(bnd) || par->n_ksub < 1;
-    cudaError_t e = strict ? launch_run_strict(a, generic, 1, s->stream, &launches_total)
-                           : launch_run_fast(a, generic, 1, s->stream, &launches_total);
+    cudaError_t e = strict ? launch_run_strict(a, generic, s->stream, &launches_total)
+                           : launch_run_fast(a, generic, s->stream, &launches_total);
     if (e != cudaSuccess) return cuda_fail(e, "time step kernel launch");
     return SEMIC_OK;
 }
@@ -665,32 +735,41 @@ extern "C" int semic_mass_balance(semic_state *now, const semic_par *par, const 
     return dropin(now, par, bnd, 0, 1, false, "mass_balance");
 }
 
-static int fill_run_args(RunArgs &a, semic_state *now, const semic_par *par, const semic_bnd *bnd, const double *forcing,
-                         int f_ld, int f_nwin, const double *vali, int day0, int ndays, double *out, int o_ld, int o_nring,
-                         int o_nvar, int out_days)
+// forcing/vali/out are TILED device series with the state's leading dimension
+static void fill_run_args(RunArgs &a, semic_state *now, const semic_par *par, const semic_bnd *bnd, const double *forcing,
+                          int f_nwin, const double *vali, int day0, int ndays, double *out, int o_nring, int o_nvar,
+                          int out_days)
 {
     std::memset(&a, 0, sizeof a);
     a.slab = now->d_slab; a.mask = now->d_mask; a.nx = now->npts; a.ld = now->ld;
     a.forcing = forcing;
-    a.f_day_stride = (long long)SEMIC_NFORCING * f_ld;
-    for (int v = 0; v < kForcingRows; ++v) a.f_var_off[v] = (long long)v * f_ld;
+    a.f_tiled = 1;
     a.f_nwin = f_nwin;
     a.f_day0 = ((day0 % f_nwin) + f_nwin) % f_nwin;
     a.vali = vali;
-    a.v_day_stride = (long long)SEMIC_NOUT * f_ld;
-    a.v_var_stride = f_ld;
     a.out = out_days > 0 ? out : nullptr;
-    a.o_day_stride = (long long)o_nvar * o_ld;
-    a.o_var_stride = o_ld;
     a.o_nring = o_nring > 0 ? o_nring : 1;
-    a.o_nvar = o_nvar;
+    a.o_nvar = o_nvar > 0 ? o_nvar : SEMIC_NOUT;
     a.out_start = ndays - out_days;
     a.ndays = ndays;
     a.eb_steps = par->n_ksub;
     a.do_mb = 1;
-    a.write_forcing_back = 1;
     a.P = make_devpar(par);
     a.B = *bnd;
+}
+
+// the state's forcing fields hold the last day's forcing after a multi-day run (as after the reference's day loop)
+static int copy_last_forcing(semic_state *now, const double *forcing, int f_nwin, int day0, int ndays)
+{
+    const int fd = (((day0 + ndays - 1) % f_nwin) + f_nwin) % f_nwin;
+    const int dst_field[kForcingRows] = {SEMIC_F_SF, SEMIC_F_RF, SEMIC_F_SWD, SEMIC_F_LWD, SEMIC_F_WIND, SEMIC_F_SP,
+                                         SEMIC_F_RHOA, SEMIC_F_QQ, -1};      // t2m is written by the kernel (mutated)
+    for (int v = 0; v < kForcingRows; ++v) {
+        if (dst_field[v] < 0) continue;
+        k_tiled_var_to_row<<<(now->npts + 255) / 256, 256, 0, now->stream>>>(forcing, now->ld, SEMIC_NFORCING, fd, v, now->npts,
+                                                                            now->d_slab + (size_t)dst_field[v] * now->ld);
+    }
+    CU(cudaGetLastError());
     return SEMIC_OK;
 }
 
@@ -712,23 +791,24 @@ extern "C" int semic_run(semic_state *now, const semic_par *par, const semic_bnd
         set_error("semic_run: output series must be 8 (or 9) x npts");
         return SEMIC_ERR_ARG;
     }
+    if (forcing->ld != now->ld || (vali && vali->ld != now->ld) || (out && out->ld != now->ld)) {
+        set_error("semic_run: leading dimensions differ");
+        return SEMIC_ERR_ARG;
+    }
     if (kernel_ms) *kernel_ms = 0.f;
     CU(cudaSetDevice(now->device));
     if (now->npts == 0 || ndays == 0) return SEMIC_OK;
     RunArgs a;
-    fill_run_args(a, now, par, bnd, forcing->d, forcing->ld, forcing->ndays, vali ? vali->d : nullptr, day0, ndays,
-                  out ? out->d : nullptr, out ? out->ld : 0, out ? out->ndays : 1, out ? out->nvar : 0, out_days);
+    fill_run_args(a, now, par, bnd, forcing->d, forcing->ndays, vali ? vali->d : nullptr, day0, ndays, out ? out->d : nullptr,
+                  out ? out->ndays : 1, out ? out->nvar : SEMIC_NOUT, out_days);
     const bool generic = any_consulted_flag(bnd) || par->n_ksub < 1;
     const int strict = opts ? opts->strict : 0;
-    int ppt = opts ? opts->ppt : 0;
-    if (ppt != 1 && ppt != 2) ppt = 1;
-    if (generic || strict) ppt = 1;
-    if (forcing->ld != now->ld || (vali && vali->ld != now->ld)) { set_error("semic_run: leading dimensions differ"); return SEMIC_ERR_ARG; }
     CU(cudaEventRecord(now->ev0, now->stream));
-    cudaError_t e = strict ? launch_run_strict(a, generic, ppt, now->stream, &launches_total)
-                           : launch_run_fast(a, generic, ppt, now->stream, &launches_total);
+    cudaError_t e = strict ? launch_run_strict(a, generic, now->stream, &launches_total)
+                           : launch_run_fast(a, generic, now->stream, &launches_total);
     if (e != cudaSuccess) return cuda_fail(e, "semic_run: kernel launch");
     CU(cudaEventRecord(now->ev1, now->stream));
+    if ((rc = copy_last_forcing(now, forcing->d, forcing->ndays, day0, ndays))) return rc;
     CU(cudaStreamSynchronize(now->stream));
     if (kernel_ms) CU(cudaEventElapsedTime(kernel_ms, now->ev0, now->ev1));
     return SEMIC_OK;
@@ -747,7 +827,9 @@ extern "C" int semic_host_free(void *p)
     return SEMIC_OK;
 }
 
-// Host-streamed run: H2D of chunk c+1 and D2H of chunk c-1 overlap the kernel of chunk c.
+// Host-streamed run: H2D of chunk c+1 and D2H of chunk c-1 overlap the kernel of chunk c.  Host buffers are SoA
+// per day (the reference's array layout); each chunk is re-tiled on the device (2 x 72 B/point-day of HBM traffic,
+// negligible next to PCIe).
 extern "C" int semic_run_host(semic_state *now, const semic_par *par, const semic_bnd *bnd, const double *h_forcing,
                               const double *h_vali, int nwin, int ldh, int ndays, double *h_out, int out_days,
                               int chunk_days, const semic_run_opts *opts, float *total_ms)
@@ -767,24 +849,23 @@ extern "C" int semic_run_host(semic_state *now, const semic_par *par, const semi
     const int ld = now->ld, npts = now->npts;
     const bool generic = any_consulted_flag(bnd) || par->n_ksub < 1;
     const int strict = opts ? opts->strict : 0;
-    int ppt = opts ? opts->ppt : 0;
-    if (ppt != 1 && ppt != 2) ppt = 1;
-    if (generic || strict) ppt = 1;
     const bool use_vali = h_vali != nullptr && generic;
 
-    double *d_f[2] = {nullptr, nullptr}, *d_v[2] = {nullptr, nullptr}, *d_o[2] = {nullptr, nullptr};
+    // per buffer set b: SoA staging (s) and tiled (t) copies of forcing f, vali v, output o
+    double *d_fs[2] = {nullptr, nullptr}, *d_ft[2] = {nullptr, nullptr}, *d_vs[2] = {nullptr, nullptr}, *d_vt[2] = {nullptr, nullptr};
+    double *d_os[2] = {nullptr, nullptr}, *d_ot[2] = {nullptr, nullptr};
     cudaStream_t s_in = nullptr, s_out = nullptr;
-    cudaEvent_t ev_in[2] = {nullptr, nullptr}, ev_k[2] = {nullptr, nullptr}, ev_o[2] = {nullptr, nullptr}, t0 = nullptr, t1 = nullptr;
-    const size_t fbytes = (size_t)chunk_days * SEMIC_NFORCING * ld * 8, obytes = (size_t)chunk_days * SEMIC_NOUT * ld * 8;
+    cudaEvent_t ev_in[2] = {nullptr, nullptr}, ev_t[2] = {nullptr, nullptr}, ev_k[2] = {nullptr, nullptr}, ev_o[2] = {nullptr, nullptr};
+    cudaEvent_t t0 = nullptr, t1 = nullptr;
+    const size_t fsb = (size_t)chunk_days * SEMIC_NFORCING * npts * 8, ftb = (size_t)chunk_days * SEMIC_NFORCING * ld * 8;
+    const size_t osb = (size_t)chunk_days * SEMIC_NOUT * npts * 8, otb = (size_t)chunk_days * SEMIC_NOUT * ld * 8;
     int status = SEMIC_OK;
     auto cleanup = [&]() {
         for (int b = 0; b < 2; ++b) {
-            if (d_f[b]) cudaFree(d_f[b]);
-            if (d_v[b]) cudaFree(d_v[b]);
-            if (d_o[b]) cudaFree(d_o[b]);
-            if (ev_in[b]) cudaEventDestroy(ev_in[b]);
-            if (ev_k[b]) cudaEventDestroy(ev_k[b]);
-            if (ev_o[b]) cudaEventDestroy(ev_o[b]);
+            double *ptrs[6] = {d_fs[b], d_ft[b], d_vs[b], d_vt[b], d_os[b], d_ot[b]};
+            for (double *p : ptrs) if (p) cudaFree(p);
+            cudaEvent_t evs[4] = {ev_in[b], ev_t[b], ev_k[b], ev_o[b]};
+            for (cudaEvent_t e : evs) if (e) cudaEventDestroy(e);
         }
         if (s_in) cudaStreamDestroy(s_in);
         if (s_out) cudaStreamDestroy(s_out);
@@ -797,11 +878,13 @@ extern "C" int semic_run_host(semic_state *now, const semic_par *par, const semi
         if (e__ != cudaSuccess) { status = cuda_fail(e__, #call); cleanup(); return status; } \
     } while (0)
     for (int b = 0; b < 2; ++b) {
-        CUX(cudaMalloc(&d_f[b], fbytes));
-        CUX(cudaMemset(d_f[b], 0, fbytes));
-        if (use_vali) { CUX(cudaMalloc(&d_v[b], obytes)); CUX(cudaMemset(d_v[b], 0, obytes)); }
-        if (out_days > 0) CUX(cudaMalloc(&d_o[b], obytes));
+        CUX(cudaMalloc(&d_fs[b], fsb));
+        CUX(cudaMalloc(&d_ft[b], ftb));
+        CUX(cudaMemset(d_ft[b], 0, ftb));
+        if (use_vali) { CUX(cudaMalloc(&d_vs[b], osb)); CUX(cudaMalloc(&d_vt[b], otb)); CUX(cudaMemset(d_vt[b], 0, otb)); }
+        if (out_days > 0) { CUX(cudaMalloc(&d_os[b], osb)); CUX(cudaMalloc(&d_ot[b], otb)); }
         CUX(cudaEventCreateWithFlags(&ev_in[b], cudaEventDisableTiming));
+        CUX(cudaEventCreateWithFlags(&ev_t[b], cudaEventDisableTiming));
         CUX(cudaEventCreateWithFlags(&ev_k[b], cudaEventDisableTiming));
         CUX(cudaEventCreateWithFlags(&ev_o[b], cudaEventDisableTiming));
     }
@@ -818,39 +901,49 @@ extern "C" int semic_run_host(semic_state *now, const semic_par *par, const semi
         const int b = c & 1;
         const int d0 = c * chunk_days;
         const int nd = (d0 + chunk_days <= ndays) ? chunk_days : ndays - d0;
-        // H2D of this chunk's forcing rows (day d -> window row d % nwin), after the kernel that last used buffer b
-        if (c >= 2) CUX(cudaStreamWaitEvent(s_in, ev_k[b], 0));
+        // H2D of this chunk's SoA rows (day d -> window row d % nwin), once the re-tiling that last read the staging is done
+        if (c >= 2) CUX(cudaStreamWaitEvent(s_in, ev_t[b], 0));
         int done = 0;
         while (done < nd) {
             const int w = (d0 + done) % nwin;
             const int run = (nd - done < nwin - w) ? nd - done : nwin - w;
-            CUX(cudaMemcpy2DAsync(d_f[b] + (size_t)done * SEMIC_NFORCING * ld, (size_t)ld * 8,
+            CUX(cudaMemcpy2DAsync(d_fs[b] + (size_t)done * SEMIC_NFORCING * npts, (size_t)npts * 8,
                                   h_forcing + (size_t)w * SEMIC_NFORCING * ldh, (size_t)ldh * 8, (size_t)npts * 8,
                                   (size_t)run * SEMIC_NFORCING, cudaMemcpyHostToDevice, s_in));
             if (use_vali)
-                CUX(cudaMemcpy2DAsync(d_v[b] + (size_t)done * SEMIC_NOUT * ld, (size_t)ld * 8,
+                CUX(cudaMemcpy2DAsync(d_vs[b] + (size_t)done * SEMIC_NOUT * npts, (size_t)npts * 8,
                                       h_vali + (size_t)w * SEMIC_NOUT * ldh, (size_t)ldh * 8, (size_t)npts * 8,
                                       (size_t)run * SEMIC_NOUT, cudaMemcpyHostToDevice, s_in));
             done += run;
         }
         CUX(cudaEventRecord(ev_in[b], s_in));
-        // kernel
+        // compute stream: re-tile, run the chunk, de-tile its output days
         CUX(cudaStreamWaitEvent(now->stream, ev_in[b], 0));
+        k_soa_to_tiled<<<1184, 256, 0, now->stream>>>(d_fs[b], npts, d_ft[b], ld, SEMIC_NFORCING, 0, nd, npts);
+        if (use_vali) k_soa_to_tiled<<<1184, 256, 0, now->stream>>>(d_vs[b], npts, d_vt[b], ld, SEMIC_NOUT, 0, nd, npts);
+        CUX(cudaGetLastError());
+        CUX(cudaEventRecord(ev_t[b], now->stream));
         const int o_lo = out_first > d0 ? out_first : d0;                 // output days of this chunk: [o_lo, d0+nd)
         const int o_n = (d0 + nd > o_lo) ? d0 + nd - o_lo : 0;
         if (o_n > 0 && c >= 2) CUX(cudaStreamWaitEvent(now->stream, ev_o[b], 0));
         RunArgs a;
-        fill_run_args(a, now, par, bnd, d_f[b], ld, nd, use_vali ? d_v[b] : nullptr, 0, nd, d_o[b], ld, chunk_days,
-                      SEMIC_NOUT, o_n);
-        cudaError_t e = strict ? launch_run_strict(a, generic, ppt, now->stream, &launches_total)
-                               : launch_run_fast(a, generic, ppt, now->stream, &launches_total);
+        fill_run_args(a, now, par, bnd, d_ft[b], nd, use_vali ? d_vt[b] : nullptr, 0, nd, d_ot[b], chunk_days, SEMIC_NOUT, o_n);
+        cudaError_t e = strict ? launch_run_strict(a, generic, now->stream, &launches_total)
+                               : launch_run_fast(a, generic, now->stream, &launches_total);
         if (e != cudaSuccess) { status = cuda_fail(e, "semic_run_host: kernel launch"); cleanup(); return status; }
-        CUX(cudaEventRecord(ev_k[b], now->stream));
-        // D2H of the chunk's output days
         if (o_n > 0) {
+            k_tiled_to_soa<<<1184, 256, 0, now->stream>>>(d_ot[b], ld, SEMIC_NOUT, 0, o_n, 0, npts, d_os[b], npts);
+            CUX(cudaGetLastError());
+        }
+        if (c == nchunks - 1) {
+            int r2 = copy_last_forcing(now, d_ft[b], nd, 0, nd);
+            if (r2) { cleanup(); return r2; }
+        }
+        CUX(cudaEventRecord(ev_k[b], now->stream));
+        if (o_n > 0) {                                                    // D2H of the chunk's output days
             CUX(cudaStreamWaitEvent(s_out, ev_k[b], 0));
-            CUX(cudaMemcpy2DAsync(h_out + (size_t)(o_lo - out_first) * SEMIC_NOUT * ldh, (size_t)ldh * 8, d_o[b],
-                                  (size_t)ld * 8, (size_t)npts * 8, (size_t)o_n * SEMIC_NOUT, cudaMemcpyDeviceToHost, s_out));
+            CUX(cudaMemcpy2DAsync(h_out + (size_t)(o_lo - out_first) * SEMIC_NOUT * ldh, (size_t)ldh * 8, d_os[b],
+                                  (size_t)npts * 8, (size_t)npts * 8, (size_t)o_n * SEMIC_NOUT, cudaMemcpyDeviceToHost, s_out));
             CUX(cudaEventRecord(ev_o[b], s_out));
         }
     }

@@ -81,8 +81,7 @@ extern "C" int semic_ensemble_cost(const semic_state *init, const semic_par *par
     CUE(cudaEventCreate(&e1));
     a.slab0 = d_slab; a.mask = d_mask; a.nx = npts; a.ld = ld;
     a.forcing = d_f; a.vali = d_v;
-    a.f_day_stride = (long long)SEMIC_NFORCING * f_ld; a.f_var_stride = f_ld;
-    a.v_day_stride = (long long)SEMIC_NOUT * v_ld; a.v_var_stride = v_ld;
+    if (f_ld != ld || v_ld != ld) { set_error("semic_ensemble_cost: leading dimensions differ"); status = SEMIC_ERR_ARG; goto done; }
     a.inv_var = d_invvar; a.pars = d_pars; a.npar = npar; a.ntime = ntime; a.nloop = nloop;
     a.partial = d_partial;
     if (npts > 0) {

@@ -13,12 +13,11 @@ namespace semic {
 enum { SCHEME_NONE = 0, SCHEME_SLATER = 1, SCHEME_DENBY = 2, SCHEME_ISBA = 3, SCHEME_ALEX = 4, SCHEME_UNKNOWN = 5,
        SCHEME_RUNTIME = 6 /* template value: switch on DevPar::scheme at run time */ };
 
-// Tile geometry of the persistent kernel: 8 consumer warps + 1 producer (TMA) warp per CTA.
-constexpr int kConsumerWarps = 8;
-constexpr int kConsumers     = kConsumerWarps * 32;      // 256
-constexpr int kThreads       = kConsumers + 32;          // 288
-constexpr int kStages        = 4;                        // days of forcing in flight per CTA
-constexpr int kLdAlign       = 1024;                     // leading dimensions (even => 16-byte rows; the last tile may be ragged)
+// Geometry of the persistent kernel: every warp owns tiles of 32 consecutive points and a private
+// shared-memory ring of kStages days fed by its own TMA bulk copies (no producer warp, no cross-warp coupling).
+constexpr int kTile          = 32;                       // points per warp tile = lanes
+constexpr int kStages        = 4;                        // days of forcing in flight per warp
+constexpr int kLdAlign       = 1024;                     // leading dimensions: multiples of this (=> whole tiles, 16-byte rows)
 constexpr int kForcingRows   = 9;
 constexpr int kExtRows       = 5;                        // tsurf alb smb melt acc overrides
 
@@ -54,33 +53,34 @@ struct DevPar {
     int    scheme;
 };
 
+// Series (forcing, validation, daily output) are stored TILE-INTERLEAVED in HBM:
+//   element (day d, var v, point i) at  base[((d*ntl + i/32)*nvar + v)*32 + i%32],  ntl = ld/32,
+// so the nvar rows a warp needs for one day are ONE contiguous block (9*256 B of forcing = one TMA bulk copy,
+// 8*256 B of output = eight stores off one base pointer).  The state slab stays SoA (its pinned host mirror
+// is what Fortran/Python array components alias).
 struct RunArgs {
     // state slab (device): field f of point i at slab[f*ld + i]
     double       *slab;
     const int    *mask;
     int           nx;
     int           ld;
-    // forcing: element (day d, var v, point i) at forcing[((day0+d) % nwin)*f_day_stride + f_var_off[v] + i]
+    // forcing: tiled series (f_tiled=1, day d -> window row (f_day0+d) % f_nwin), or the slab's own SoA forcing
+    // fields (f_tiled=0: variable v of point i at forcing[f_var_off[v] + i]; the drop-in single-day call)
     const double *forcing;
-    long long     f_day_stride;
+    int           f_tiled;
     long long     f_var_off[kForcingRows];
     int           f_nwin;
     int           f_day0;
-    // external override fields (validation layout, 8 rows per day) or NULL
+    // external override fields (tiled validation series, 8 rows per day) or NULL
     const double *vali;
-    long long     v_day_stride;
-    long long     v_var_stride;
-    // daily output ring or NULL: row ((d - out_start) % o_nring), var v, point i
+    // daily output ring (tiled, o_nvar rows per day) or NULL: day d of the run goes to row (d - out_start) % o_nring
     double       *out;
-    long long     o_day_stride;
-    long long     o_var_stride;
     int           o_nring;
     int           o_nvar;       // 8, or 9 with the branch bitmap
     int           out_start;    // first day (0-based within this run) that is written
     int           ndays;
     int           eb_steps;     // sub-steps of energy_balance per day (n_ksub; 1 for energy_balance alone; 0 = skip)
     int           do_mb;        // run mass_balance
-    int           write_forcing_back;   // store the last day's forcing into the slab (multi-day runs)
     DevPar        P;
     semic_bnd     B;
 };
@@ -90,9 +90,8 @@ struct EnsArgs {
     const double *slab0;        // initial state [31][ld]
     const int    *mask;
     int           nx, ld;
-    const double *forcing;      // [ntime][9][ldf]
-    const double *vali;         // [ntime][8][ldf]
-    long long     f_day_stride, f_var_stride, v_day_stride, v_var_stride;
+    const double *forcing;      // tiled [ntime][ld/32][9][32]
+    const double *vali;         // tiled [ntime][ld/32][8][32]
     const double *inv_var;      // [4][ld]  1/var of vali stt, melt, smb, swnet (zero variance -> inf, like utils.f90:36)
     const DevPar *pars;         // [npar]
     int           npar;
@@ -102,8 +101,8 @@ struct EnsArgs {
 };
 
 // implemented once per arithmetic mode (semic_kernels_fast.cu / semic_kernels_strict.cu)
-cudaError_t launch_run_fast(const RunArgs &a, bool generic, int ppt, cudaStream_t st, int *launches);
-cudaError_t launch_run_strict(const RunArgs &a, bool generic, int ppt, cudaStream_t st, int *launches);
+cudaError_t launch_run_fast(const RunArgs &a, bool generic, cudaStream_t st, int *launches);
+cudaError_t launch_run_strict(const RunArgs &a, bool generic, cudaStream_t st, int *launches);
 // inv_var and partial are scratch buffers owned by the caller; sumsq_dev receives npar doubles
 cudaError_t launch_vali_invvar(const EnsArgs &a, double *inv_var, cudaStream_t st);
 cudaError_t launch_ensemble_fast(const EnsArgs &a, double *sumsq_dev, cudaStream_t st);

@@ -556,7 +556,6 @@ DEVI void mbar_wait(uint32_t bar, uint32_t parity)
         "WAIT_%=:\n"
         "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, %2;\n"
         "@p bra DONE_%=;\n"
-        "nanosleep.u32 800;\n"
         "bra WAIT_%=;\n"
         "DONE_%=:\n"
         "}\n" ::"r"(bar), "r"(parity), "r"(0x989680u)   // suspend-time hint: sleep in hardware, do not spin
@@ -573,213 +572,208 @@ DEVI void tma_load_1d(uint32_t smem_dst, const void *gmem_src, uint32_t bytes, u
 // ------------------------------------------------------------------------------------------------
 // the persistent multi-day kernel
 // ------------------------------------------------------------------------------------------------
-template <bool GENERIC, int PPT, int CW>
+DEVI void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+template <bool GENERIC, int WPC>
 struct RunSmem {
-    static constexpr int T = CW * 32 * PPT;
     static constexpr int ROWS = kForcingRows + (GENERIC ? kExtRows : 0);
-    static constexpr int STAGES = (PPT == 1) ? kStages : 3;
-    static constexpr size_t stage_bytes = (size_t)ROWS * T * sizeof(double);
-    static constexpr size_t bar_bytes = 2 * STAGES * sizeof(uint64_t);
-    static constexpr size_t bytes = stage_bytes * STAGES + bar_bytes + 64 * sizeof(double);      // ring, barriers, exp table
+    static constexpr int STAGES = kStages;
+    static constexpr size_t stage_bytes = (size_t)ROWS * kTile * sizeof(double);          // 2304 B (3584 B generic)
+    static constexpr size_t ring_bytes = stage_bytes * STAGES * WPC;
+    static constexpr size_t bar_bytes = (size_t)WPC * STAGES * sizeof(uint64_t);
+    static constexpr size_t bytes = ring_bytes + bar_bytes + 64 * sizeof(double);          // rings, barriers, exp table
 };
 
 // validation-layout rows that feed the overrides tsurf, alb, smb, melt, acc (example.f90:103-107)
 __device__ __constant__ int c_ext_var[kExtRows] = {SEMIC_O_STT, SEMIC_O_ALB, SEMIC_O_SMB, SEMIC_O_MELT, SEMIC_O_ACC};
 
-template <int SCHEME, bool GENERIC, int PPT, int MINB, bool BR, int CW>
-__global__ void __launch_bounds__(CW * 32 + 32, MINB) k_run(const __grid_constant__ RunArgs a)
+// lane 0 of a warp: one day's forcing (and override rows) of this warp's tile -> one stage of the warp's ring
+template <bool GENERIC>
+DEVI void issue_day(const RunArgs &a, const long long tile, const int fd, const long long ntl, const uint32_t dst,
+                    const uint32_t bar, const bool (&ext_on)[kExtRows], const int n_ext)
 {
-    using SM = RunSmem<GENERIC, PPT, CW>;
-    constexpr int T = SM::T;
-    constexpr int ROWS = SM::ROWS;
+    constexpr uint32_t rowb = kTile * (uint32_t)sizeof(double);
+    mbar_expect_tx(bar, rowb * (uint32_t)(kForcingRows + (GENERIC ? n_ext : 0)));
+    if (a.f_tiled) {
+        tma_load_1d(dst, a.forcing + ((long long)fd * ntl + tile) * (kForcingRows * kTile), kForcingRows * rowb, bar);
+    } else {
+        const double *src = a.forcing + tile * kTile;
+#pragma unroll
+        for (int v = 0; v < kForcingRows; ++v) tma_load_1d(dst + v * rowb, src + a.f_var_off[v], rowb, bar);
+    }
+    if (GENERIC) {
+        const double *vs = a.vali + ((long long)fd * ntl + tile) * (SEMIC_NOUT * kTile);
+#pragma unroll
+        for (int e = 0; e < kExtRows; ++e)
+            if (ext_on[e]) tma_load_1d(dst + (kForcingRows + e) * rowb, vs + c_ext_var[e] * kTile, rowb, bar);
+    }
+}
+
+template <int SCHEME, bool GENERIC, int MINB, bool BR, int WPC>
+__global__ void __launch_bounds__(WPC * 32, MINB) k_run(const __grid_constant__ RunArgs a)
+{
+    using SM = RunSmem<GENERIC, WPC>;
     constexpr int NST = SM::STAGES;
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    double *sbuf = reinterpret_cast<double *>(smem_raw);
-    const uint32_t sbuf_u32 = smem_u32(smem_raw);
-    const uint32_t full_u32 = sbuf_u32 + (uint32_t)(SM::stage_bytes * NST);     // full[s] at +8*s, empty[s] at +8*(NST+s)
-    const uint32_t empty_u32 = full_u32 + 8u * NST;
-
-    double *tab = reinterpret_cast<double *>(smem_raw + SM::stage_bytes * NST + SM::bar_bytes);
-
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
-    if (threadIdx.x == 0) {
-        for (int s = 0; s < NST; ++s) {
-            mbar_init(full_u32 + 8u * s, 1);
-            mbar_init(empty_u32 + 8u * s, CW);
-        }
+    const uint32_t smem_u = smem_u32(smem_raw);
+    const uint32_t ring_u = smem_u + (uint32_t)(warp * NST) * (uint32_t)SM::stage_bytes;     // this warp's ring
+    const uint32_t bar_u = smem_u + (uint32_t)SM::ring_bytes + (uint32_t)(warp * NST) * 8u;  // this warp's barriers
+    const double *ring = reinterpret_cast<const double *>(smem_raw) + (size_t)(warp * NST) * SM::ROWS * kTile;
+    double *tab = reinterpret_cast<double *>(smem_raw + SM::ring_bytes + SM::bar_bytes);
+
+    if (lane == 0) {
+        for (int s = 0; s < NST; ++s) mbar_init(bar_u + 8u * s, 1);
         mbar_fence_init();
     }
     if (threadIdx.x < 64) tab[threadIdx.x] = c_exp2_tab[threadIdx.x];
     __syncthreads();
 
-    const int ntiles = (a.nx + T - 1) / T;
     bool ext_on[kExtRows] = {false, false, false, false, false};
+    int n_ext = 0;
     if (GENERIC && a.vali != nullptr) {
         ext_on[0] = a.B.tsurf != 0; ext_on[1] = a.B.alb != 0; ext_on[2] = a.B.smb != 0;
         ext_on[3] = a.B.melt != 0;  ext_on[4] = a.B.acc != 0;
+        for (int e = 0; e < kExtRows; ++e) n_ext += ext_on[e] ? 1 : 0;
     }
 
-    if (warp == CW) {
-        // ---------------- producer: one lane feeds the ring with TMA bulk copies ----------------
-        if (lane == 0) {
-            int nrows = kForcingRows;
-            if (GENERIC) for (int e = 0; e < kExtRows; ++e) if (ext_on[e]) ++nrows;
-            int stage = 0;
-            uint32_t phase = 0;
-            for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-                const long long p0 = (long long)tile * T;
-                // ragged last tile: rows are ld long (ld is even, so the copy stays a multiple of 16 bytes)
-                const long long left = (long long)a.ld - p0;
-                const uint32_t rowb = (uint32_t)(left < T ? left : T) * (uint32_t)sizeof(double);
-                const uint32_t nbytes = rowb * (uint32_t)nrows;
-                int fd = a.f_day0 % a.f_nwin;
-                for (int d = 0; d < a.ndays; ++d) {
-                    mbar_wait(empty_u32 + 8u * stage, phase ^ 1u);
-                    mbar_expect_tx(full_u32 + 8u * stage, nbytes);
-                    const uint32_t dst = sbuf_u32 + (uint32_t)stage * (uint32_t)SM::stage_bytes;
-                    const double *src = a.forcing + (long long)fd * a.f_day_stride + p0;
-#pragma unroll
-                    for (int v = 0; v < kForcingRows; ++v)
-                        tma_load_1d(dst + v * T * 8u, src + a.f_var_off[v], rowb, full_u32 + 8u * stage);
-                    if (GENERIC) {
-                        const double *vs = a.vali + (long long)fd * a.v_day_stride + p0;
-#pragma unroll
-                        for (int e = 0; e < kExtRows; ++e)
-                            if (ext_on[e])
-                                tma_load_1d(dst + (kForcingRows + e) * T * 8u, vs + c_ext_var[e] * a.v_var_stride, rowb,
-                                            full_u32 + 8u * stage);
-                    }
-                    if (++fd == a.f_nwin) fd = 0;
-                    if (++stage == NST) { stage = 0; phase ^= 1u; }
-                }
-            }
-        }
-        return;
-    }
-
-    // ---------------- consumers ----------------
-    const int tid = threadIdx.x;          // 0..CW*32-1
     const long long ld = a.ld;
+    const long long ntl = ld / kTile;                            // tiles per series row
+    const long long ntiles = ((long long)a.nx + kTile - 1) / kTile;
+    const long long nwarps = (long long)gridDim.x * WPC;
     int stage = 0;
     uint32_t phase = 0;
-    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-        const long long i0 = (long long)tile * T + (long long)tid * PPT;
-        Pt s[PPT];
-        bool valid[PPT];
-#pragma unroll
-        for (int p = 0; p < PPT; ++p) {
-            const long long i = i0 + p;
-            valid[p] = i < a.nx;
-            const long long ii = valid[p] ? i : 0;
-            const double *S = a.slab + ii;
-            s[p].mask = valid[p] ? a.mask[ii] : 0;
-            s[p].tsurf    = S[SEMIC_F_TSURF * ld];
-            s[p].hsnow    = S[SEMIC_F_HSNOW * ld];
-            s[p].hice     = S[SEMIC_F_HICE * ld];
-            s[p].alb      = S[SEMIC_F_ALB * ld];
-            s[p].alb_snow = S[SEMIC_F_ALB_SNOW * ld];
-            s[p].qmr_res  = S[SEMIC_F_QMR_RES * ld];
-            if (GENERIC) {
-                s[p].melt = S[SEMIC_F_MELT * ld];
-                s[p].melted_snow = S[SEMIC_F_MELTED_SNOW * ld];
-                s[p].melted_ice = S[SEMIC_F_MELTED_ICE * ld];
-                s[p].refr = S[SEMIC_F_REFR * ld];
-                s[p].smb = S[SEMIC_F_SMB * ld];
-                s[p].acc = S[SEMIC_F_ACC * ld];
-                s[p].lhf = S[SEMIC_F_LHF * ld];
-                s[p].shf = S[SEMIC_F_SHF * ld];
-                s[p].lwu = S[SEMIC_F_LWU * ld];
-                s[p].subl = S[SEMIC_F_SUBL * ld];
-                s[p].evap = S[SEMIC_F_EVAP * ld];
-                s[p].smb_snow = S[SEMIC_F_SMB_SNOW * ld];
-                s[p].smb_ice = S[SEMIC_F_SMB_ICE * ld];
-                s[p].runoff = S[SEMIC_F_RUNOFF * ld];
-                s[p].qmr = S[SEMIC_F_QMR * ld];
-                s[p].amp = S[SEMIC_F_AMP * ld];
-            } else {
-                s[p].melt = s[p].melted_snow = s[p].melted_ice = s[p].refr = s[p].smb = s[p].acc = 0.0;
-                s[p].lhf = s[p].shf = s[p].lwu = s[p].subl = s[p].evap = s[p].smb_snow = s[p].smb_ice = 0.0;
-                s[p].runoff = s[p].qmr = s[p].amp = 0.0;
+
+    for (long long tile = (long long)blockIdx.x * WPC + warp; tile < ntiles; tile += nwarps) {
+        const long long i = tile * kTile + lane;
+        const bool valid = i < a.nx;
+        const long long ii = valid ? i : 0;
+
+        // prefetch the first days of this tile into the (empty) ring, in stage order
+        int fd_issue = a.f_day0 % a.f_nwin;
+        int d_issue = 0;
+        if (lane == 0) {
+            int s = stage;
+            for (; d_issue < NST && d_issue < a.ndays; ++d_issue) {
+                issue_day<GENERIC>(a, tile, fd_issue, ntl, ring_u + (uint32_t)s * (uint32_t)SM::stage_bytes, bar_u + 8u * s,
+                                   ext_on, n_ext);
+                if (++fd_issue == a.f_nwin) fd_issue = 0;
+                if (++s == NST) s = 0;
             }
-            s[p].t2m = 0.0;
         }
 
-        // daily output: ring slot advances by one per written day (no modulo in the loop)
-        double *oday = (a.out != nullptr) ? a.out + i0 : nullptr;
+        Pt s;
+        {
+            const double *S = a.slab + ii;
+            s.mask = valid ? a.mask[ii] : 0;
+            s.tsurf    = S[SEMIC_F_TSURF * ld];
+            s.hsnow    = S[SEMIC_F_HSNOW * ld];
+            s.hice     = S[SEMIC_F_HICE * ld];
+            s.alb      = S[SEMIC_F_ALB * ld];
+            s.alb_snow = S[SEMIC_F_ALB_SNOW * ld];
+            s.qmr_res  = S[SEMIC_F_QMR_RES * ld];
+            if (GENERIC) {
+                s.melt = S[SEMIC_F_MELT * ld];
+                s.melted_snow = S[SEMIC_F_MELTED_SNOW * ld];
+                s.melted_ice = S[SEMIC_F_MELTED_ICE * ld];
+                s.refr = S[SEMIC_F_REFR * ld];
+                s.smb = S[SEMIC_F_SMB * ld];
+                s.acc = S[SEMIC_F_ACC * ld];
+                s.lhf = S[SEMIC_F_LHF * ld];
+                s.shf = S[SEMIC_F_SHF * ld];
+                s.lwu = S[SEMIC_F_LWU * ld];
+                s.subl = S[SEMIC_F_SUBL * ld];
+                s.evap = S[SEMIC_F_EVAP * ld];
+                s.smb_snow = S[SEMIC_F_SMB_SNOW * ld];
+                s.smb_ice = S[SEMIC_F_SMB_ICE * ld];
+                s.runoff = S[SEMIC_F_RUNOFF * ld];
+                s.qmr = S[SEMIC_F_QMR * ld];
+                s.amp = S[SEMIC_F_AMP * ld];
+            } else {
+                s.melt = s.melted_snow = s.melted_ice = s.refr = s.smb = s.acc = 0.0;
+                s.lhf = s.shf = s.lwu = s.subl = s.evap = s.smb_snow = s.smb_ice = 0.0;
+                s.runoff = s.qmr = s.amp = 0.0;
+            }
+            s.t2m = 0.0;
+        }
+
+        // daily output: tiled ring, this lane's column of the warp's block; the slot advances by one per written day
+        const long long o_block = (long long)a.o_nvar * kTile;                    // doubles per tile-day
+        double *oday = (a.out != nullptr) ? a.out + tile * o_block + lane : nullptr;
+        const long long o_day = ntl * o_block;
         int oslot = 0;
-        const long long ovs = a.o_var_stride;
 
         for (int d = 0; d < a.ndays; ++d) {
-            mbar_wait(full_u32 + 8u * stage, phase);
-            const double *row = sbuf + (size_t)stage * ROWS * T + tid * PPT;
+            mbar_wait(bar_u + 8u * stage, phase);
+            const double *row = ring + (size_t)stage * SM::ROWS * kTile + lane;
             const bool write_out = (oday != nullptr) && (d >= a.out_start);
-#pragma unroll
-            for (int p = 0; p < PPT; ++p) {
-                if (valid[p]) {
-                    if (GENERIC) {                                     // example.f90:103-107
-                        if (ext_on[0]) s[p].tsurf = row[(kForcingRows + 0) * T + p];
-                        if (ext_on[1]) s[p].alb   = row[(kForcingRows + 1) * T + p];
-                        if (ext_on[2]) s[p].smb   = row[(kForcingRows + 2) * T + p];
-                        if (ext_on[3]) s[p].melt  = row[(kForcingRows + 3) * T + p];
-                        if (ext_on[4]) s[p].acc   = row[(kForcingRows + 4) * T + p];
-                    }
-                    double swd;
-                    const unsigned br = point_day<SCHEME, GENERIC, BR>(s[p], row + p, T, a.P, a.B, a.eb_steps, a.do_mb, swd, SEMIC_STRICT ? nullptr : tab);
-                    if (write_out) {                                   // example.f90:117-122
-                        double *o = oday + p;
-                        o[0] = s[p].tsurf;                 o += ovs;   // SEMIC_O_STT
-                        o[0] = s[p].alb;                   o += ovs;   // SEMIC_O_ALB
-                        o[0] = swd * (1.0 - s[p].alb);     o += ovs;   // SEMIC_O_SWNET
-                        o[0] = s[p].smb;                   o += ovs;   // SEMIC_O_SMB
-                        o[0] = s[p].melt;                  o += ovs;   // SEMIC_O_MELT
-                        o[0] = s[p].acc;                   o += ovs;   // SEMIC_O_ACC
-                        o[0] = s[p].shf;                   o += ovs;   // SEMIC_O_SHF
-                        o[0] = s[p].lhf;                               // SEMIC_O_LHF
-                        if (BR) { o += ovs; o[0] = (double)br; }       // SEMIC_O_BRANCH (series with 9 rows)
-                    }
+            if (valid) {
+                if (GENERIC) {                                         // example.f90:103-107
+                    if (ext_on[0]) s.tsurf = row[(kForcingRows + 0) * kTile];
+                    if (ext_on[1]) s.alb   = row[(kForcingRows + 1) * kTile];
+                    if (ext_on[2]) s.smb   = row[(kForcingRows + 2) * kTile];
+                    if (ext_on[3]) s.melt  = row[(kForcingRows + 3) * kTile];
+                    if (ext_on[4]) s.acc   = row[(kForcingRows + 4) * kTile];
+                }
+                double swd;
+                const unsigned br = point_day<SCHEME, GENERIC, BR>(s, row, kTile, a.P, a.B, a.eb_steps, a.do_mb, swd,
+                                                                   SEMIC_STRICT ? nullptr : tab);
+                if (write_out) {                                       // example.f90:117-122
+                    oday[SEMIC_O_STT * kTile]   = s.tsurf;
+                    oday[SEMIC_O_ALB * kTile]   = s.alb;
+                    oday[SEMIC_O_SWNET * kTile] = swd * (1.0 - s.alb);
+                    oday[SEMIC_O_SMB * kTile]   = s.smb;
+                    oday[SEMIC_O_MELT * kTile]  = s.melt;
+                    oday[SEMIC_O_ACC * kTile]   = s.acc;
+                    oday[SEMIC_O_SHF * kTile]   = s.shf;
+                    oday[SEMIC_O_LHF * kTile]   = s.lhf;
+                    if (BR) oday[SEMIC_O_BRANCH * kTile] = (double)br;  // series with 9 rows
                 }
             }
-            // every shared-memory read of this stage is done: hand it back to the producer
+            // all lanes are done reading this stage: refill it with day d + NST (generic-proxy reads are ordered
+            // before the async-proxy write by the warp barrier + proxy fence)
             __syncwarp();
-            if (lane == 0) mbar_arrive(empty_u32 + 8u * stage);
+            if (lane == 0 && d_issue < a.ndays) {
+                fence_proxy_async();
+                issue_day<GENERIC>(a, tile, fd_issue, ntl, ring_u + (uint32_t)stage * (uint32_t)SM::stage_bytes,
+                                   bar_u + 8u * stage, ext_on, n_ext);
+                ++d_issue;
+                if (++fd_issue == a.f_nwin) fd_issue = 0;
+            }
             if (++stage == NST) { stage = 0; phase ^= 1u; }
             if (write_out) {
-                oday += a.o_day_stride;
-                if (++oslot == a.o_nring) { oslot = 0; oday -= (long long)a.o_nring * a.o_day_stride; }
+                oday += o_day;
+                if (++oslot == a.o_nring) { oslot = 0; oday -= (long long)a.o_nring * o_day; }
             }
         }
 
         // final state of the tile: all 23 non-forcing fields, as after the reference's last call
-        if (a.ndays > 0) {
-#pragma unroll
-            for (int p = 0; p < PPT; ++p) {
-                if (!valid[p]) continue;
-                double *S = a.slab + (i0 + p);
-                S[SEMIC_F_T2M * ld] = s[p].t2m;
-                S[SEMIC_F_TSURF * ld] = s[p].tsurf;
-                S[SEMIC_F_HSNOW * ld] = s[p].hsnow;
-                S[SEMIC_F_HICE * ld] = s[p].hice;
-                S[SEMIC_F_ALB * ld] = s[p].alb;
-                S[SEMIC_F_ALB_SNOW * ld] = s[p].alb_snow;
-                S[SEMIC_F_MELT * ld] = s[p].melt;
-                S[SEMIC_F_MELTED_SNOW * ld] = s[p].melted_snow;
-                S[SEMIC_F_MELTED_ICE * ld] = s[p].melted_ice;
-                S[SEMIC_F_REFR * ld] = s[p].refr;
-                S[SEMIC_F_SMB * ld] = s[p].smb;
-                S[SEMIC_F_ACC * ld] = s[p].acc;
-                S[SEMIC_F_LHF * ld] = s[p].lhf;
-                S[SEMIC_F_SHF * ld] = s[p].shf;
-                S[SEMIC_F_LWU * ld] = s[p].lwu;
-                S[SEMIC_F_SUBL * ld] = s[p].subl;
-                S[SEMIC_F_EVAP * ld] = s[p].evap;
-                S[SEMIC_F_SMB_SNOW * ld] = s[p].smb_snow;
-                S[SEMIC_F_SMB_ICE * ld] = s[p].smb_ice;
-                S[SEMIC_F_RUNOFF * ld] = s[p].runoff;
-                S[SEMIC_F_QMR * ld] = s[p].qmr;
-                S[SEMIC_F_QMR_RES * ld] = s[p].qmr_res;
-                S[SEMIC_F_AMP * ld] = s[p].amp;
-            }
+        if (a.ndays > 0 && valid) {
+            double *S = a.slab + i;
+            S[SEMIC_F_T2M * ld] = s.t2m;
+            S[SEMIC_F_TSURF * ld] = s.tsurf;
+            S[SEMIC_F_HSNOW * ld] = s.hsnow;
+            S[SEMIC_F_HICE * ld] = s.hice;
+            S[SEMIC_F_ALB * ld] = s.alb;
+            S[SEMIC_F_ALB_SNOW * ld] = s.alb_snow;
+            S[SEMIC_F_MELT * ld] = s.melt;
+            S[SEMIC_F_MELTED_SNOW * ld] = s.melted_snow;
+            S[SEMIC_F_MELTED_ICE * ld] = s.melted_ice;
+            S[SEMIC_F_REFR * ld] = s.refr;
+            S[SEMIC_F_SMB * ld] = s.smb;
+            S[SEMIC_F_ACC * ld] = s.acc;
+            S[SEMIC_F_LHF * ld] = s.lhf;
+            S[SEMIC_F_SHF * ld] = s.shf;
+            S[SEMIC_F_LWU * ld] = s.lwu;
+            S[SEMIC_F_SUBL * ld] = s.subl;
+            S[SEMIC_F_EVAP * ld] = s.evap;
+            S[SEMIC_F_SMB_SNOW * ld] = s.smb_snow;
+            S[SEMIC_F_SMB_ICE * ld] = s.smb_ice;
+            S[SEMIC_F_RUNOFF * ld] = s.runoff;
+            S[SEMIC_F_QMR * ld] = s.qmr;
+            S[SEMIC_F_QMR_RES * ld] = s.qmr_res;
+            S[SEMIC_F_AMP * ld] = s.amp;
         }
     }
 }
@@ -824,6 +818,7 @@ __global__ void __launch_bounds__(32 * kEnsParticles) k_ensemble(const EnsArgs a
     Pt s;
     const double *S = a.slab0 + ii;
     const long long ld = a.ld;
+    const long long ntl = ld / kTile;
     s.mask = a.mask[ii];
     s.tsurf = S[SEMIC_F_TSURF * ld];
     s.hsnow = S[SEMIC_F_HSNOW * ld];
@@ -838,16 +833,16 @@ __global__ void __launch_bounds__(32 * kEnsParticles) k_ensemble(const EnsArgs a
     for (int k = 0; k < a.nloop; ++k) {
         const bool lastloop = (k == a.nloop - 1);
         for (int n = 0; n < a.ntime; ++n) {
-            const double *row = a.forcing + (long long)n * a.f_day_stride + ii;
+            const double *row = a.forcing + ((long long)n * ntl + tile) * (kForcingRows * kTile) + lane;
             double swd;
-            point_day<SCHEME_RUNTIME, false, false>(s, row, a.f_var_stride, P, B, P.n_ksub, 1, swd, tab);
+            point_day<SCHEME_RUNTIME, false, false>(s, row, kTile, P, B, P.n_ksub, 1, swd, tab);
             if (lastloop) {                                              // run_particles.f90:148-157
-                const double *v = a.vali + (long long)n * a.v_day_stride + ii;
+                const double *v = a.vali + ((long long)n * ntl + tile) * (SEMIC_NOUT * kTile) + lane;
                 double d[4];
-                d[0] = s.tsurf - v[SEMIC_O_STT * a.v_var_stride];
-                d[1] = s.melt - v[SEMIC_O_MELT * a.v_var_stride];
-                d[2] = s.smb - v[SEMIC_O_SMB * a.v_var_stride];
-                d[3] = swd * (1.0 - s.alb) - v[SEMIC_O_SWNET * a.v_var_stride];
+                d[0] = s.tsurf - v[SEMIC_O_STT * kTile];
+                d[1] = s.melt - v[SEMIC_O_MELT * kTile];
+                d[2] = s.smb - v[SEMIC_O_SMB * kTile];
+                d[3] = swd * (1.0 - s.alb) - v[SEMIC_O_SWNET * kTile];
 #pragma unroll
                 for (int q = 0; q < 4; ++q) {
                     if (n == 0) d0[q] = d[q];
@@ -874,14 +869,14 @@ __global__ void __launch_bounds__(32 * kEnsParticles) k_ensemble(const EnsArgs a
 }
 
 // 1/var of the validation series per point for stt, melt, smb, swnet (utils.f90:33-34: two-pass)
-__global__ void k_vali_invvar(const double *vali, long long day_stride, long long var_stride, int ntime, int nx, int ld,
-                              double *inv_var)
+__global__ void k_vali_invvar(const double *vali, int ntime, int nx, int ld, double *inv_var)
 {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= nx) return;
     const int vars[4] = {SEMIC_O_STT, SEMIC_O_MELT, SEMIC_O_SMB, SEMIC_O_SWNET};
+    const long long day_stride = (long long)(ld / kTile) * SEMIC_NOUT * kTile;
     for (int q = 0; q < 4; ++q) {
-        const double *x = vali + vars[q] * var_stride + i;
+        const double *x = vali + ((long long)(i / kTile) * SEMIC_NOUT + vars[q]) * kTile + (i % kTile);
         double sum = 0.0;
         for (int n = 0; n < ntime; ++n) sum += x[(long long)n * day_stride];
         const double avg = sum / ntime;

@@ -3,6 +3,7 @@
 #define SEMIC_STRICT 0
 #define SEMIC_MODE_NS fast_mode
 #include <cstdlib>
+#include <cstring>
 #include "semic_kernels.cuh"
 
 namespace semic {
@@ -34,34 +35,26 @@ __global__ void k_elementals(int which, const double *in0, const double *in1, co
 }
 }  // namespace fast_mode
 
-cudaError_t launch_run_fast(const RunArgs &a, bool generic, int ppt, cudaStream_t st, int *launches)
+cudaError_t launch_run_fast(const RunArgs &a, bool generic, cudaStream_t st, int *launches)
 {
     if (launches) ++*launches;
-    if (generic) return fast_mode::launch_scheme<true, 1, 1>(a, st);
-    // tuning knob: resident CTAs per SM the kernel is compiled for (register budget 65536/(288*MINB))
-    const char *e = getenv("SEMIC_MINB");
-    int minb = e ? atoi(e) : 2;
-    if (minb < 1 || minb > 3) minb = 2;
-    if (ppt == 2) {
-        const char *c2 = getenv("SEMIC_CW");
-        if (c2 && atoi(c2) == 7) return fast_mode::launch_scheme<false, 2, 2, 7>(a, st);
-        return fast_mode::launch_scheme<false, 2, 1, 15>(a, st);
+    if (generic) return fast_mode::launch_scheme<true, 1, 8>(a, st);
+    // tuning knob SEMIC_SHAPE = "<warps per CTA>x<CTAs per SM>" (default 8x3: 24 warps per SM at <= 80 registers)
+    const char *e = getenv("SEMIC_SHAPE");
+    const int shape = e ? atoi(e) * 10 + (strchr(e, 'x') ? atoi(strchr(e, 'x') + 1) : 0) : 83;
+    switch (shape) {
+        case 82:  return fast_mode::launch_scheme<false, 2, 8>(a, st);       // 16 warps, <=128 regs
+        case 242: case 241: return fast_mode::launch_scheme<false, 1, 24>(a, st);      // one CTA of 24 warps
+        case 162: return fast_mode::launch_scheme<false, 2, 16>(a, st);      // 32 warps, <=64 regs
+        case 84:  return fast_mode::launch_scheme<false, 4, 8>(a, st);       // 32 warps, <=64 regs
+        default:  return fast_mode::launch_scheme<false, 3, 8>(a, st);
     }
-    const char *c = getenv("SEMIC_CW");
-    const int cw = c ? atoi(c) : 20;      // default: one CTA of 20 consumer warps + 1 producer per SM (profiles/r01_tuning.md)
-    if (cw == 20) return fast_mode::launch_scheme<false, 1, 1, 20>(a, st);
-    if (cw == 10) return fast_mode::launch_scheme<false, 1, 2, 10>(a, st);
-    if (cw == 6) return fast_mode::launch_scheme<false, 1, 3, 6>(a, st);
-    if (minb == 1) return fast_mode::launch_scheme<false, 1, 1>(a, st);
-    if (minb == 3) return fast_mode::launch_scheme<false, 1, 3>(a, st);
-    return fast_mode::launch_scheme<false, 1, 2>(a, st);
 }
 
 cudaError_t launch_vali_invvar(const EnsArgs &a, double *inv_var, cudaStream_t st)
 {
     if (a.nx <= 0) return cudaSuccess;
-    fast_mode::k_vali_invvar<<<(a.nx + 127) / 128, 128, 0, st>>>(a.vali, a.v_day_stride, a.v_var_stride, a.ntime, a.nx, a.ld,
-                                                                 inv_var);
+    fast_mode::k_vali_invvar<<<(a.nx + 127) / 128, 128, 0, st>>>(a.vali, a.ntime, a.nx, a.ld, inv_var);
     return cudaGetLastError();
 }
 

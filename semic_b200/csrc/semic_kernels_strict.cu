@@ -9,10 +9,9 @@ namespace strict_mode {
 #include "semic_launch.inl"
 }  // namespace strict_mode
 
-cudaError_t launch_run_strict(const RunArgs &a, bool generic, int ppt, cudaStream_t st, int *launches)
+cudaError_t launch_run_strict(const RunArgs &a, bool generic, cudaStream_t st, int *launches)
 {
-    (void)ppt;
     if (launches) ++*launches;
-    return generic ? strict_mode::launch_scheme<true, 1, 1>(a, st) : strict_mode::launch_scheme<false, 1, 1>(a, st);
+    return generic ? strict_mode::launch_scheme<true, 1, 8>(a, st) : strict_mode::launch_scheme<false, 1, 8>(a, st);
 }
 }  // namespace semic

@@ -1,12 +1,12 @@
 // semic_launch.inl -- host-side launcher of k_run for the arithmetic mode of the including TU.
 // (included inside namespace semic::SEMIC_MODE_NS)
 
-template <int SCHEME, bool GENERIC, int PPT, int MINB, bool BR, int CW = kConsumerWarps>
+template <int SCHEME, bool GENERIC, int MINB, bool BR, int WPC>
 static cudaError_t launch_one(const RunArgs &a, cudaStream_t st)
 {
-    auto kern = k_run<SCHEME, GENERIC, PPT, MINB, BR, CW>;
-    constexpr size_t smem = RunSmem<GENERIC, PPT, CW>::bytes;
-    constexpr int kThreads = CW * 32 + 32;
+    auto kern = k_run<SCHEME, GENERIC, MINB, BR, WPC>;
+    constexpr size_t smem = RunSmem<GENERIC, WPC>::bytes;
+    constexpr int kThreads = WPC * 32;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     int dev = 0, nsm = 0, occ = 0;
@@ -14,28 +14,28 @@ static cudaError_t launch_one(const RunArgs &a, cudaStream_t st)
     if ((e = cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev)) != cudaSuccess) return e;
     if ((e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, kThreads, smem)) != cudaSuccess) return e;
     if (occ < 1) return cudaErrorLaunchOutOfResources;
-    constexpr int T = RunSmem<GENERIC, PPT, CW>::T;
-    const int ntiles = (a.nx + T - 1) / T;
-    int grid = nsm * occ;                       // persistent: one CTA per resident slot, each walks its tiles
-    if (grid > ntiles) grid = ntiles;
+    const long long ntiles = ((long long)a.nx + kTile - 1) / kTile;
+    long long grid = (long long)nsm * occ;      // persistent: one CTA per resident slot, every warp walks its tiles
+    const long long need = (ntiles + WPC - 1) / WPC;
+    if (grid > need) grid = need;
     if (grid < 1) return cudaSuccess;
-    kern<<<grid, kThreads, smem, st>>>(a);
+    kern<<<(unsigned)grid, kThreads, smem, st>>>(a);
     return cudaGetLastError();
 }
 
 // The branch bitmap (9th output row, flip report) costs ~20 instructions per point-day, so it is a separate
 // instantiation; it uses the run-time scheme switch to keep the number of kernels down.
-template <bool GENERIC, int PPT, int MINB, int CW = kConsumerWarps>
+template <bool GENERIC, int MINB, int WPC>
 static cudaError_t launch_scheme(const RunArgs &a, cudaStream_t st)
 {
-    if (a.out != nullptr && a.o_nvar > SEMIC_NOUT) return launch_one<SCHEME_RUNTIME, GENERIC, 1, 1, true>(a, st);
-    if (GENERIC) return launch_one<SCHEME_RUNTIME, GENERIC, PPT, MINB, false>(a, st);      // scheme resolved at run time
+    if (a.out != nullptr && a.o_nvar > SEMIC_NOUT) return launch_one<SCHEME_RUNTIME, GENERIC, 1, true, 8>(a, st);
+    if (GENERIC) return launch_one<SCHEME_RUNTIME, GENERIC, MINB, false, WPC>(a, st);      // scheme resolved at run time
     switch (a.P.scheme) {
-        case SCHEME_NONE:   return launch_one<SCHEME_NONE, GENERIC, PPT, MINB, false, CW>(a, st);
-        case SCHEME_SLATER: return launch_one<SCHEME_SLATER, GENERIC, PPT, MINB, false, CW>(a, st);
-        case SCHEME_DENBY:  return launch_one<SCHEME_DENBY, GENERIC, PPT, MINB, false, CW>(a, st);
-        case SCHEME_ISBA:   return launch_one<SCHEME_ISBA, GENERIC, PPT, MINB, false, CW>(a, st);
-        case SCHEME_ALEX:   return launch_one<SCHEME_ALEX, GENERIC, PPT, MINB, false, CW>(a, st);
-        default:            return launch_one<SCHEME_UNKNOWN, GENERIC, PPT, MINB, false, CW>(a, st);
+        case SCHEME_NONE:   return launch_one<SCHEME_NONE, GENERIC, MINB, false, WPC>(a, st);
+        case SCHEME_SLATER: return launch_one<SCHEME_SLATER, GENERIC, MINB, false, WPC>(a, st);
+        case SCHEME_DENBY:  return launch_one<SCHEME_DENBY, GENERIC, MINB, false, WPC>(a, st);
+        case SCHEME_ISBA:   return launch_one<SCHEME_ISBA, GENERIC, MINB, false, WPC>(a, st);
+        case SCHEME_ALEX:   return launch_one<SCHEME_ALEX, GENERIC, MINB, false, WPC>(a, st);
+        default:            return launch_one<SCHEME_UNKNOWN, GENERIC, MINB, false, WPC>(a, st);
     }
 }

@@ -20,13 +20,12 @@ for k in (3, 24):
     for key, v in bench.par_dict("slater", k).items():
         setattr(par, key, v)
     par.tsticsub = par.tstic / k
-    for cw, minb, ppt in ((8, 2, 1), (8, 3, 1), (20, 1, 1), (15, 1, 2), (7, 2, 2)):
-        os.environ["SEMIC_MINB"] = str(minb)
-        os.environ["SEMIC_CW"] = str(cw)
-        engine.run(st, par, bnd, forcing, 8, out=out, out_days=8, ppt=ppt)
-        ts = [engine.run(st, par, bnd, forcing, days, out=out, out_days=days, ppt=ppt) for _ in range(3)]
+    for shape in ("8x3", "8x2", "24x1", "16x2", "8x4"):
+        os.environ["SEMIC_SHAPE"] = shape
+        engine.run(st, par, bnd, forcing, 8, out=out, out_days=8)
+        ts = [engine.run(st, par, bnd, forcing, days, out=out, out_days=days) for _ in range(3)]
         t = min(ts)
         rate = N * days / (t * 1e-3)
-        print("k=%2d cw=%2d minb=%d ppt=%d: %.2f ms  %.2f G pt-days/s  %.0f GB/s (M1 136 B)  no-out:" % (k, cw, minb, ppt, t, rate / 1e9, rate * 136 / 1e9), end=" ")
-        t0 = min(engine.run(st, par, bnd, forcing, days, ppt=ppt) for _ in range(2))
+        print("k=%2d shape=%s: %.2f ms  %.2f G pt-days/s  %.0f GB/s (M1 136 B)  no-out:" % (k, shape, t, rate / 1e9, rate * 136 / 1e9), end=" ")
+        t0 = min(engine.run(st, par, bnd, forcing, days) for _ in range(2))
         print("%.2f G pt-days/s" % (N * days / (t0 * 1e-3) / 1e9), flush=True)
