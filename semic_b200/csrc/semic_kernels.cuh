@@ -189,6 +189,9 @@ DEVI double esat(double ts, bool ice)
 }
 
 // latent_heat_flux, surface_physics.f90:393-430; returns q = subl (ice) or evap (water) in kg/(s m2)
+// ALLG: the caller guarantees ts <= t0 (the point is gated, :201): at ts == t0 the argument a*x/(b+x) is 0 for either
+// pair (a,b), so the ice constants serve both branches bit for bit and the two selects disappear.
+template <bool ALLG = false>
 DEVI double latent_q(double ts, double wind_clh_rho, double shum, double sp, bool ice, const double *tab)
 {
     (void)tab;
@@ -197,8 +200,8 @@ DEVI double latent_q(double ts, double wind_clh_rho, double shum, double sp, boo
     const double shum_sat = fdiv(es * c_eps, (es * (c_eps - 1.0)) + sp);
 #else
     // 611.2 folded into the two eps factors: es*eps/(es*(eps-1)+sp)
-    const double a = ice ? kc[18] : kc[20];
-    const double b = ice ? kc[19] : kc[21];
+    const double a = (ALLG || ice) ? kc[18] : kc[20];
+    const double b = (ALLG || ice) ? kc[19] : kc[21];
     const double x = ts - kc[14];
     const double e = fexp_t((a * x) * frcp(b + x), tab);
     const double shum_sat = (e * kc[15]) * frcp(fma(e, kc[16], sp));
@@ -302,11 +305,69 @@ struct Pt {
 
 #define BND(x) (GENERIC && (B.x != 0))
 
+// n_ksub x energy_balance (surface_physics.f90:158-214) for one point; state in registers
+template <bool GENERIC, bool ALLG, int UNR>
+DEVI void energy_substeps(double &ts, double &t2m, double &shf, double &lhf, double &subl, double &evap, double &lwu,
+                          double &q_last, double &over, bool &ice_last, const double shf_c, const double lhf_c,
+                          const double rad, const double qq, const double sp, const double qmr_res, const bool gate,
+                          const int nsub, const DevPar &P, const semic_bnd &B, const double *tab)
+{
+#pragma unroll UNR
+    for (int k = 0; k < nsub; ++k) {
+        if (!BND(shf)) shf = shf_c * (ts - t2m);                               // :173
+        if (!BND(lhf)) {                                                       // :179-185
+#if SEMIC_STRICT
+            const bool ice = ts < c_t0;                                        // :415
+            const double q = latent_q<false>(ts, lhf_c, qq, sp, ice, tab);
+            lhf = q * (ice ? c_cls : c_clv);                                   // :421,:428
+#else
+            const bool ice = ts < kc[14];
+            const double q = latent_q<ALLG>(ts, lhf_c, qq, sp, ice, tab);
+            lhf = q * (ice ? kc[22] : kc[23]);
+#endif
+            q_last = q;
+            ice_last = ice;
+            if (GENERIC) { subl = ice ? q : 0.0; evap = ice ? 0.0 : q; }
+        }
+        if (GENERIC) subl = fdiv(subl, c_rhow);                                // :186 (every sub-step, Q3)
+#if SEMIC_STRICT
+        lwu = longwave_upward(ts, c_sigm);                                     // :191
+#else
+        lwu = longwave_upward(ts, kc[17]);
+#endif
+        const double qsb = (((rad - lwu) - shf) - lhf) - qmr_res;              // :194
+        over = 0.0;                                                            // :197
+        if (!BND(tsurf)) {                                                     // :198
+#if SEMIC_STRICT
+            ts = ts + fdiv(qsb * P.tsticsub, P.ceff);                          // :199
+            if (gate && ts > c_t0) {                                           // :201-204
+                over = ts - c_t0;
+                ts = c_t0;
+            }
+#else
+            ts = fma(qsb, P.sub_over_ceff, ts);
+            if (gate && ts > kc[14]) {
+                over = ts - kc[14];
+                ts = kc[14];
+            }
+#endif
+        }
+        if (gate) {                                                            // :209-211 (Q1: forcing t2m is mutated)
+#if SEMIC_STRICT
+            t2m = t2m + fdiv((shf + lhf) * P.tsticsub, P.ceff);
+#else
+            t2m = fma(shf + lhf, P.sub_over_ceff, t2m);
+#endif
+        }
+    }
+}
+
+
 // `row` points at this point's column of the day's forcing (a shared-memory stage in k_run, global
 // memory in k_ensemble): variable v is row[v*T].  Values are read where they are first needed (LDS
 // is cheap, registers across the sub-step loop are not); `swd_out` returns the day's shortwave for
 // the swnet diagnostic.
-template <int SCHEME, bool GENERIC, bool WANT_BRANCH>
+template <int SCHEME, bool GENERIC, bool WANT_BRANCH, int UNR = 2>
 DEVI unsigned point_day(Pt &s, const double *row, const long long T, const DevPar &P, const semic_bnd &B,
                         const int eb_steps, const int do_mb, double &swd_out, const double *tab)
 {
@@ -329,58 +390,19 @@ DEVI unsigned point_day(Pt &s, const double *row, const long long T, const DevPa
         const double lhf_c  = (P.clh * wind) * rhoa;
         const double rad    = ((1.0 - s.alb) * swd) + row[SEMIC_V_LWD * T];
         const double qq = row[SEMIC_V_QQ * T], sp = row[SEMIC_V_SP * T];
-        const double qmr_res = s.qmr_res;
         double q_last = 0.0, over = 0.0;
-        bool ice_last = false, any = false;
+        bool ice_last = false;
         const int nsub = GENERIC ? eb_steps : P.n_ksub;
-        for (int k = 0; k < nsub; ++k) {
-            any = true;
-            if (!BND(shf)) shf = shf_c * (ts - t2m);                               // :173
-            if (!BND(lhf)) {                                                       // :179-185
-#if SEMIC_STRICT
-                const bool ice = ts < c_t0;                                        // :415
-                const double q = latent_q(ts, lhf_c, qq, sp, ice, tab);
-                lhf = q * (ice ? c_cls : c_clv);                                   // :421,:428
-#else
-                const bool ice = ts < kc[14];
-                const double q = latent_q(ts, lhf_c, qq, sp, ice, tab);
-                lhf = q * (ice ? kc[22] : kc[23]);
-#endif
-                q_last = q;
-                ice_last = ice;
-                if (GENERIC) { subl = ice ? q : 0.0; evap = ice ? 0.0 : q; }
-            }
-            if (GENERIC) subl = fdiv(subl, c_rhow);                                // :186 (every sub-step, Q3)
-#if SEMIC_STRICT
-            lwu = longwave_upward(ts, c_sigm);                                     // :191
-#else
-            lwu = longwave_upward(ts, kc[17]);
-#endif
-            const double qsb = (((rad - lwu) - shf) - lhf) - qmr_res;              // :194
-            over = 0.0;                                                            // :197
-            if (!BND(tsurf)) {                                                     // :198
-#if SEMIC_STRICT
-                ts = ts + fdiv(qsb * P.tsticsub, P.ceff);                          // :199
-                if (gate && ts > c_t0) {                                           // :201-204
-                    over = ts - c_t0;
-                    ts = c_t0;
-                }
-#else
-                ts = fma(qsb, P.sub_over_ceff, ts);
-                if (gate && ts > kc[14]) {
-                    over = ts - kc[14];
-                    ts = kc[14];
-                }
-#endif
-            }
-            if (gate) {                                                            // :209-211 (Q1: forcing t2m is mutated)
-#if SEMIC_STRICT
-                t2m = t2m + fdiv((shf + lhf) * P.tsticsub, P.ceff);
-#else
-                t2m = fma(shf + lhf, P.sub_over_ceff, t2m);
-#endif
-            }
-        }
+        const bool any = nsub > 0;
+        // gated points never exceed t0 (:201-204), which removes the ei/ew constant selects (see latent_q); taken when
+        // every active lane of the warp is gated, e.g. the interior of an ice sheet
+        const bool allg = !GENERIC && !SEMIC_STRICT && __all_sync(__activemask(), gate && ts <= c_t0);
+        if (allg)
+            energy_substeps<GENERIC, true, UNR>(ts, t2m, shf, lhf, subl, evap, lwu, q_last, over, ice_last, shf_c, lhf_c, rad,
+                                                qq, sp, s.qmr_res, gate, nsub, P, B, tab);
+        else
+            energy_substeps<GENERIC, false, UNR>(ts, t2m, shf, lhf, subl, evap, lwu, q_last, over, ice_last, shf_c, lhf_c, rad,
+                                                 qq, sp, s.qmr_res, gate, nsub, P, B, tab);
         if (any) {
             // only the last sub-step's qmr survives (:197, Q2)
 #if SEMIC_STRICT
@@ -428,7 +450,7 @@ DEVI unsigned point_day(Pt &s, const double *row, const long long T, const DevPa
             qcold = dmax1(0.0, fdiv(fabs(below) * P.ceff, P.tstic));
 #else
             qmelt = dmax1(0.0, above * P.ceff_over_tstic);
-            qcold = dmax1(0.0, fabs(below) * P.ceff_over_tstic);
+            qcold = fabs(below) * P.ceff_over_tstic;              // dmax1(0,|x|) == |x| for every x
 #endif
         }
 #if SEMIC_STRICT
@@ -438,7 +460,10 @@ DEVI unsigned point_day(Pt &s, const double *row, const long long T, const DevPa
         if (!BND(melt)) melt = qmelt * P.inv_rhow_clm;
         // IEEE quotient: when all snow melts, hsnow - (hsnow/tstic)*tstic decides between "bare" and a
         // one-ulp ghost snow layer (which keeps the :201 gate on over land); keep the reference's rounding
-        const double hs_rate = __ddiv_rn(hsnow, P.tstic);
+        // (one Newton refinement of hsnow*(1/tstic) is the correctly rounded quotient up to ~2^-50 odds: 3 instructions
+        //  instead of the ~15 of the general IEEE division routine)
+        const double hs_q = hsnow * P.inv_tstic;
+        const double hs_rate = fma(fma(-hs_q, P.tstic, hsnow), P.inv_tstic, hs_q);
 #endif
         melted_snow = dmin1(melt, hs_rate);                                         // :269
         melted_ice  = melt - melted_snow;                                          // :270
@@ -609,7 +634,7 @@ DEVI void issue_day(const RunArgs &a, const long long tile, const int fd, const 
     }
 }
 
-template <int SCHEME, bool GENERIC, int MINB, bool BR, int WPC>
+template <int SCHEME, bool GENERIC, int MINB, bool BR, int WPC, int UNR = 2>
 __global__ void __launch_bounds__(WPC * 32, MINB) k_run(const __grid_constant__ RunArgs a)
 {
     using SM = RunSmem<GENERIC, WPC>;
@@ -717,8 +742,8 @@ __global__ void __launch_bounds__(WPC * 32, MINB) k_run(const __grid_constant__ 
                     if (ext_on[4]) s.acc   = row[(kForcingRows + 4) * kTile];
                 }
                 double swd;
-                const unsigned br = point_day<SCHEME, GENERIC, BR>(s, row, kTile, a.P, a.B, a.eb_steps, a.do_mb, swd,
-                                                                   SEMIC_STRICT ? nullptr : tab);
+                const unsigned br = point_day<SCHEME, GENERIC, BR, UNR>(s, row, kTile, a.P, a.B, a.eb_steps, a.do_mb, swd,
+                                                                        SEMIC_STRICT ? nullptr : tab);
                 if (write_out) {                                       // example.f90:117-122
                     oday[SEMIC_O_STT * kTile]   = s.tsurf;
                     oday[SEMIC_O_ALB * kTile]   = s.alb;

@@ -1,10 +1,10 @@
 // semic_launch.inl -- host-side launcher of k_run for the arithmetic mode of the including TU.
 // (included inside namespace semic::SEMIC_MODE_NS)
 
-template <int SCHEME, bool GENERIC, int MINB, bool BR, int WPC>
+template <int SCHEME, bool GENERIC, int MINB, bool BR, int WPC, int UNR = 2>
 static cudaError_t launch_one(const RunArgs &a, cudaStream_t st)
 {
-    auto kern = k_run<SCHEME, GENERIC, MINB, BR, WPC>;
+    auto kern = k_run<SCHEME, GENERIC, MINB, BR, WPC, UNR>;
     constexpr size_t smem = RunSmem<GENERIC, WPC>::bytes;
     constexpr int kThreads = WPC * 32;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -25,17 +25,17 @@ static cudaError_t launch_one(const RunArgs &a, cudaStream_t st)
 
 // The branch bitmap (9th output row, flip report) costs ~20 instructions per point-day, so it is a separate
 // instantiation; it uses the run-time scheme switch to keep the number of kernels down.
-template <bool GENERIC, int MINB, int WPC>
+template <bool GENERIC, int MINB, int WPC, int UNR = 2>
 static cudaError_t launch_scheme(const RunArgs &a, cudaStream_t st)
 {
     if (a.out != nullptr && a.o_nvar > SEMIC_NOUT) return launch_one<SCHEME_RUNTIME, GENERIC, 1, true, 8>(a, st);
     if (GENERIC) return launch_one<SCHEME_RUNTIME, GENERIC, MINB, false, WPC>(a, st);      // scheme resolved at run time
     switch (a.P.scheme) {
-        case SCHEME_NONE:   return launch_one<SCHEME_NONE, GENERIC, MINB, false, WPC>(a, st);
-        case SCHEME_SLATER: return launch_one<SCHEME_SLATER, GENERIC, MINB, false, WPC>(a, st);
-        case SCHEME_DENBY:  return launch_one<SCHEME_DENBY, GENERIC, MINB, false, WPC>(a, st);
-        case SCHEME_ISBA:   return launch_one<SCHEME_ISBA, GENERIC, MINB, false, WPC>(a, st);
-        case SCHEME_ALEX:   return launch_one<SCHEME_ALEX, GENERIC, MINB, false, WPC>(a, st);
-        default:            return launch_one<SCHEME_UNKNOWN, GENERIC, MINB, false, WPC>(a, st);
+        case SCHEME_NONE:   return launch_one<SCHEME_NONE, GENERIC, MINB, false, WPC, UNR>(a, st);
+        case SCHEME_SLATER: return launch_one<SCHEME_SLATER, GENERIC, MINB, false, WPC, UNR>(a, st);
+        case SCHEME_DENBY:  return launch_one<SCHEME_DENBY, GENERIC, MINB, false, WPC, UNR>(a, st);
+        case SCHEME_ISBA:   return launch_one<SCHEME_ISBA, GENERIC, MINB, false, WPC, UNR>(a, st);
+        case SCHEME_ALEX:   return launch_one<SCHEME_ALEX, GENERIC, MINB, false, WPC, UNR>(a, st);
+        default:            return launch_one<SCHEME_UNKNOWN, GENERIC, MINB, false, WPC, UNR>(a, st);
     }
 }
