@@ -46,6 +46,7 @@ cudaError_t launch_run_fast(const RunArgs &a, bool generic, cudaStream_t st, int
         case 82:  return fast_mode::launch_scheme<false, 2, 8>(a, st);       // 16 warps, <=128 regs
         case 242: case 241:                                                  // one CTA of 24 warps
             return a.P.n_ksub >= 8 ? fast_mode::launch_scheme<false, 1, 24, 4>(a, st) : fast_mode::launch_scheme<false, 1, 24, 2>(a, st);
+        case 201: return fast_mode::launch_scheme<false, 1, 20>(a, st);      // one CTA of 20 warps, <=96 regs
         case 162: return fast_mode::launch_scheme<false, 2, 16>(a, st);      // 32 warps, <=64 regs
         case 84:  return fast_mode::launch_scheme<false, 4, 8>(a, st);       // 32 warps, <=64 regs
         default:  return fast_mode::launch_scheme<false, 3, 8>(a, st);

@@ -464,3 +464,31 @@ def test_ensemble_with_nccl_communicator_single_rank():
     b = driver.run_particles(pop, names, forc, vali, mask, init, ntime, nloop)
     check(lib().semic_comm_free(comm))
     assert a == b
+
+
+# ------------------------------------------------------------------------------------------------------------
+# the example program end to end (example/example.f90 with its namelist): files in, example.out out
+# ------------------------------------------------------------------------------------------------------------
+def test_run_example_program(tmp_path):
+    from semic_b200 import driver
+    from oracle import binding as ob
+    forc, vali = util.load_fixture("transect")
+    (tmp_path / "data").mkdir()
+    np.savetxt(tmp_path / "data" / "transect_input.txt", forc.reshape(365, -1))
+    np.savetxt(tmp_path / "data" / "transect_output.txt", vali.reshape(365, -1))
+    nml = open(util.GOLDEN + "/example.nml").read().replace("nloop = 100", "nloop = 3")
+    (tmp_path / "example.namelist").write_text(nml)
+    out, now, par, bnd = driver.run_example(str(tmp_path / "example.namelist"))
+    # oracle twin of example.f90:74-127
+    mask = np.array([1, 1, 1, 2, 2, 2, 2], dtype=np.int32)
+    S, m = util.init_slab(7, mask, hsnow=5.0, alb=np.float64(np.float32(0.8)))
+    ref, br = ob.run(S, m, ob.make_par(util.PAR_EXAMPLE), ob.make_bnd(), forc, 3 * 365, vali=vali, out_days=365)
+    written = np.loadtxt(tmp_path / "example.out")                      # plot_example.py reads it the same way
+    assert written.shape == (365, 56)
+    assert np.array_equal(written.reshape(365, 8, 7), out)              # %24.16E round-trips doubles
+    ice = mask == 2
+    errs = util.out_errors(out[:, :, ice], ref[:, :, ice])
+    assert max(errs.values()) <= TOL, errs
+    # the state object holds the last day, like the reference's `surface%now` after the loop
+    assert np.allclose(np.array(now.tsurf)[ice], ref[-1, 0, ice], rtol=1e-12)
+    assert np.array_equal(np.array(now.sf), forc[364, 0, :]) and np.array_equal(np.array(now.qq), forc[364, 7, :])
