@@ -640,7 +640,7 @@ __global__ void __launch_bounds__(WPC * 32, MINB) k_run(const __grid_constant__ 
     using SM = RunSmem<GENERIC, WPC>;
     constexpr int NST = SM::STAGES;
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    const int warp = threadIdx.x >> 5;
+    const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);   // warp-uniform for the compiler: ring/barrier/tile arithmetic moves to the uniform datapath
     const int lane = threadIdx.x & 31;
     const uint32_t smem_u = smem_u32(smem_raw);
     const uint32_t ring_u = smem_u + (uint32_t)(warp * NST) * (uint32_t)SM::stage_bytes;     // this warp's ring
@@ -804,6 +804,159 @@ __global__ void __launch_bounds__(WPC * 32, MINB) k_run(const __grid_constant__ 
 }
 
 #if !SEMIC_STRICT
+// ------------------------------------------------------------------------------------------------
+// the benchmarked instantiation of the persistent kernel: no boundary flags, tiled forcing, 8 daily rows
+// ------------------------------------------------------------------------------------------------
+// Same physics (point_day) and the same warp-private TMA rings as k_run; what differs is the shell around it:
+//  * the warp index is broadcast with a shuffle, so tile, ring, barrier and forcing addresses are warp-uniform to the
+//    compiler: they live in uniform registers and UBLKCP takes them directly (k_run needs an ELECT/R2UR waterfall);
+//  * every lane counts the issued days (only the copy itself is elected), nothing in the loop re-derives an address
+//    from threadIdx;
+//  * the final state is stored from inside the day loop (last day only), so the 15 diagnostics that are not daily
+//    output are not live across iterations (and one copy of the day body keeps chunked runs bit-identical);
+//  * lanes beyond nx compute on the padding columns (ld is a multiple of 1024) instead of branching around the day.
+DEVI bool elect_one()
+{
+    uint32_t pred;
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "elect.sync _|p, 0xffffffff;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}\n" : "=r"(pred));
+    return pred != 0;
+}
+
+template <int SCHEME, int WPC, int UNR>
+__global__ void __launch_bounds__(WPC * 32, 1) k_run_lean(const __grid_constant__ RunArgs a)
+{
+    using SM = RunSmem<false, WPC>;
+    constexpr int NST = SM::STAGES;
+    constexpr uint32_t SB = (uint32_t)SM::stage_bytes;
+    constexpr int FBLK = kForcingRows * kTile;                   // doubles per tile-day of forcing
+    constexpr int OBLK = SEMIC_NOUT * kTile;                     // doubles per tile-day of output
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
+    const int lane = threadIdx.x & 31;
+    const uint32_t smem_u = smem_u32(smem_raw);
+    const uint32_t ring_u = smem_u + (uint32_t)(warp * NST) * SB;
+    const uint32_t bar_u = smem_u + (uint32_t)SM::ring_bytes + (uint32_t)(warp * NST) * 8u;
+    const double *ring = reinterpret_cast<const double *>(smem_raw + (size_t)(warp * NST) * SB) + lane;
+    double *tab = reinterpret_cast<double *>(smem_raw + SM::ring_bytes + SM::bar_bytes);
+
+    if (lane == 0) {
+        for (int s = 0; s < NST; ++s) mbar_init(bar_u + 8u * s, 1);
+        mbar_fence_init();
+    }
+    if (threadIdx.x < 64) tab[threadIdx.x] = c_exp2_tab[threadIdx.x];
+    __syncthreads();
+
+    const long long ld = a.ld;
+    const long long ntl = ld / kTile;
+    const long long ntiles = ((long long)a.nx + kTile - 1) / kTile;
+    const long long nwarps = (long long)gridDim.x * WPC;
+    const long long f_day = ntl * FBLK;                          // doubles per forcing day
+    const long long o_day = ntl * OBLK;
+    const int ndays = a.ndays;
+    __builtin_assume(a.P.n_ksub >= 1);                           // guaranteed by the launcher (n_ksub < 1 runs k_run)
+    const int ostart = (a.out != nullptr) ? a.out_start : ndays;
+    uint32_t stage = 0, phase = 0;
+
+    for (long long tile = (long long)blockIdx.x * WPC + warp; tile < ntiles; tile += nwarps) {
+        const double *ftile = a.forcing + tile * FBLK;
+        int fd = a.f_day0 % a.f_nwin;
+        int d_issue = 0;
+        {
+            uint32_t s = stage;
+            const int npre = ndays < NST ? ndays : NST;
+            for (; d_issue < npre; ++d_issue) {
+                if (elect_one()) {
+                    mbar_expect_tx(bar_u + 8u * s, SB);
+                    tma_load_1d(ring_u + s * SB, ftile + (long long)fd * f_day, SB, bar_u + 8u * s);
+                }
+                if (++fd == a.f_nwin) fd = 0;
+                if (++s == NST) s = 0;
+            }
+        }
+
+        const long long i = tile * kTile + lane;
+        Pt s;
+        {
+            const double *S = a.slab + i;                        // the slab has ld >= ntiles*32 columns
+            s.mask = a.mask[i];
+            s.tsurf    = S[SEMIC_F_TSURF * ld];
+            s.hsnow    = S[SEMIC_F_HSNOW * ld];
+            s.hice     = S[SEMIC_F_HICE * ld];
+            s.alb      = S[SEMIC_F_ALB * ld];
+            s.alb_snow = S[SEMIC_F_ALB_SNOW * ld];
+            s.qmr_res  = S[SEMIC_F_QMR_RES * ld];
+            s.melt = s.melted_snow = s.melted_ice = s.refr = s.smb = s.acc = 0.0;
+            s.lhf = s.shf = s.lwu = s.subl = s.evap = s.smb_snow = s.smb_ice = 0.0;
+            s.runoff = s.qmr = s.amp = s.t2m = 0.0;
+        }
+        double *oday = a.out + tile * OBLK + lane;
+        int oslot = 0;
+
+        auto one_day = [&](const int d) {
+            mbar_wait(bar_u + 8u * stage, phase);
+            const double *row = ring + (size_t)stage * (SB / sizeof(double));
+            double swd;
+            point_day<SCHEME, false, false, UNR>(s, row, kTile, a.P, a.B, 0, 1, swd, tab);
+            if (d >= ostart) {                                   // example.f90:117-122
+                oday[SEMIC_O_STT * kTile]   = s.tsurf;
+                oday[SEMIC_O_ALB * kTile]   = s.alb;
+                oday[SEMIC_O_SWNET * kTile] = swd * (1.0 - s.alb);
+                oday[SEMIC_O_SMB * kTile]   = s.smb;
+                oday[SEMIC_O_MELT * kTile]  = s.melt;
+                oday[SEMIC_O_ACC * kTile]   = s.acc;
+                oday[SEMIC_O_SHF * kTile]   = s.shf;
+                oday[SEMIC_O_LHF * kTile]   = s.lhf;
+                oday += o_day;
+                if (++oslot == a.o_nring) { oslot = 0; oday -= (long long)a.o_nring * o_day; }
+            }
+            if (d == ndays - 1 && i < a.nx) {   // final state: all 23 non-forcing fields, as after the reference's last call
+                double *S = a.slab + i;
+                S[SEMIC_F_T2M * ld] = s.t2m;
+                S[SEMIC_F_TSURF * ld] = s.tsurf;
+                S[SEMIC_F_HSNOW * ld] = s.hsnow;
+                S[SEMIC_F_HICE * ld] = s.hice;
+                S[SEMIC_F_ALB * ld] = s.alb;
+                S[SEMIC_F_ALB_SNOW * ld] = s.alb_snow;
+                S[SEMIC_F_MELT * ld] = s.melt;
+                S[SEMIC_F_MELTED_SNOW * ld] = s.melted_snow;
+                S[SEMIC_F_MELTED_ICE * ld] = s.melted_ice;
+                S[SEMIC_F_REFR * ld] = s.refr;
+                S[SEMIC_F_SMB * ld] = s.smb;
+                S[SEMIC_F_ACC * ld] = s.acc;
+                S[SEMIC_F_LHF * ld] = s.lhf;
+                S[SEMIC_F_SHF * ld] = s.shf;
+                S[SEMIC_F_LWU * ld] = s.lwu;
+                S[SEMIC_F_SUBL * ld] = s.subl;
+                S[SEMIC_F_EVAP * ld] = s.evap;
+                S[SEMIC_F_SMB_SNOW * ld] = s.smb_snow;
+                S[SEMIC_F_SMB_ICE * ld] = s.smb_ice;
+                S[SEMIC_F_RUNOFF * ld] = s.runoff;
+                S[SEMIC_F_QMR * ld] = s.qmr;
+                S[SEMIC_F_QMR_RES * ld] = s.qmr_res;
+                S[SEMIC_F_AMP * ld] = s.amp;
+            }
+            // every lane has consumed its column of the stage (the loaded values fed the arithmetic above): refill it
+            __syncwarp();
+            if (d_issue < ndays) {
+                if (elect_one()) {
+                    mbar_expect_tx(bar_u + 8u * stage, SB);
+                    tma_load_1d(ring_u + stage * SB, ftile + (long long)fd * f_day, SB, bar_u + 8u * stage);
+                }
+                ++d_issue;
+                if (++fd == a.f_nwin) fd = 0;
+            }
+            if (++stage == NST) { stage = 0; phase ^= 1u; }
+        };
+
+        for (int d = 0; d < ndays; ++d) one_day(d);
+    }
+}
+
 // ------------------------------------------------------------------------------------------------
 // ensemble misfit (optimize/run_particles.f90:104-178 + utils.f90:23-42), config 5
 // ------------------------------------------------------------------------------------------------

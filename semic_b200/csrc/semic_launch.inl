@@ -39,3 +39,38 @@ static cudaError_t launch_scheme(const RunArgs &a, cudaStream_t st)
         default:            return launch_one<SCHEME_UNKNOWN, GENERIC, MINB, false, WPC, UNR>(a, st);
     }
 }
+
+#if !SEMIC_STRICT
+// k_run_lean: the plain (no boundary flag) tiled-forcing run with 8 daily rows, n_ksub >= 1
+template <int SCHEME, int WPC, int UNR>
+static cudaError_t launch_lean_one(const RunArgs &a, cudaStream_t st)
+{
+    auto kern = k_run_lean<SCHEME, WPC, UNR>;
+    constexpr size_t smem = RunSmem<false, WPC>::bytes;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    int dev = 0, nsm = 0;
+    if ((e = cudaGetDevice(&dev)) != cudaSuccess) return e;
+    if ((e = cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev)) != cudaSuccess) return e;
+    const long long ntiles = ((long long)a.nx + kTile - 1) / kTile;
+    long long grid = nsm;                       // persistent: one CTA per SM, every warp walks its tiles
+    const long long need = (ntiles + WPC - 1) / WPC;
+    if (grid > need) grid = need;
+    if (grid < 1) return cudaSuccess;
+    kern<<<(unsigned)grid, WPC * 32, smem, st>>>(a);
+    return cudaGetLastError();
+}
+
+template <int WPC, int UNR>
+static cudaError_t launch_lean(const RunArgs &a, cudaStream_t st)
+{
+    switch (a.P.scheme) {
+        case SCHEME_NONE:   return launch_lean_one<SCHEME_NONE, WPC, UNR>(a, st);
+        case SCHEME_SLATER: return launch_lean_one<SCHEME_SLATER, WPC, UNR>(a, st);
+        case SCHEME_DENBY:  return launch_lean_one<SCHEME_DENBY, WPC, UNR>(a, st);
+        case SCHEME_ISBA:   return launch_lean_one<SCHEME_ISBA, WPC, UNR>(a, st);
+        case SCHEME_ALEX:   return launch_lean_one<SCHEME_ALEX, WPC, UNR>(a, st);
+        default:            return launch_lean_one<SCHEME_UNKNOWN, WPC, UNR>(a, st);
+    }
+}
+#endif
