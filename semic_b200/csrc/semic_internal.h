@@ -46,11 +46,14 @@ struct DevPar {
     double inv_rhow_clm;     // 1/(rhow*clm)
     double inv_hcrit_eps;    // 1/(hcrit+epsil)
     double inv_amp;          // 1/amp
+    double inv_amp2;         // 1/(amp*amp)
     double inv_mcrit;        // 1/mcrit
     double isba_new;         // tstic/(w_crn/rhow)*(alb_smax-alb_smin)
     double frz_rhow_clm;     // (1-f_rz)*rhow*clm
     int    n_ksub;
     int    scheme;
+    int    falb_clamp;       // hsmax/(hcrit+epsil) >= 700: clamp the argument of the f_alb exponential
+    int    pad_;
 };
 
 // Series (forcing, validation, daily output) are stored TILE-INTERLEAVED in HBM:

@@ -102,18 +102,16 @@ __device__ __constant__ double kt[8] = {92.33248261689366, 6755399441055744.0, -
 DEVI double fdiv(double n, double d) { return n / d; }    // CUDA double division is IEEE round-to-nearest
 DEVI double fexp(double x) { return exp(x); }
 #else
-// reciprocal from the MUFU.RCP64H seed + two Newton steps (operands here are normal, far from
-// 0/inf: temperatures, pressures, positive parameters).  ~1 ulp.
+// reciprocal from the MUFU.RCP64H seed (it reads the upper 32 bits only: relative error e ~ 2^-20) refined by
+// r0*(1 + e + e^2), which leaves e^3 ~ 2^-60, below the rounding of the result; 3 DFMA.  Operands here are normal and
+// far from 0/inf (temperatures, pressures, positive parameters).
 DEVI double frcp(double d)
 {
     double r;
     asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(d));
-    // two Newton steps; the second residual is e*e exactly (1 - d*r1 = e^2), which shortens the dependent chain
     const double e = fma(-d, r, 1.0);
-    const double e2 = e * e;
-    r = fma(r, e, r);
-    r = fma(r, e2, r);
-    return r;
+    const double t = fma(e, e, e);
+    return fma(r, t, r);
 }
 DEVI double fdiv(double n, double d) { return n * frcp(d); }
 // exp for |x| < 700 without special-case handling: Cody-Waite reduction by ln2 and the
@@ -160,6 +158,45 @@ DEVI double fexp_t(double x, const double *tab)
     const double q = fma(p45, r2, p23);
     const double p = fma(q, r2, p01) * tab[n & 63];
     return __hiloint2double(__double2hiint(p) + ((n >> 6) << 20), __double2loint(p));
+}
+// asin(s) = s + s*z*R(z), z = s*s <= 1/4: degree-11 interpolant of R at the Chebyshev nodes of [0, 1/4]
+// (relative error of asin 5.6e-17 before rounding); coefficients highest degree first
+__device__ __constant__ double ka[14] = {
+    0.028169218060881414, -0.010749050339697808, 0.01603551434914882, 0.0078029494773533175,
+    0.011875494382636922, 0.013929652902326633, 0.017355259955786323, 0.02237204763174451,
+    0.03038194736709848, 0.044642857103423646, 0.07500000000020764, 0.1666666666666665,
+    3.141592653589793238462643, 1.5707963267948966};   // 12, 13: pi, pi/2
+// sqrt(z) for a normal z > 0: MUFU.RSQ64H seed, two coupled Newton steps, one residual correction
+DEVI double fsqrt_pos(double z)
+{
+    double y;
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(z));
+    double g = z * y, h = 0.5 * y;
+    double r = fma(-h, g, 0.5);
+    g = fma(g, r, g);
+    h = fma(h, r, h);
+    r = fma(-h, g, 0.5);
+    g = fma(g, r, g);
+    h = fma(h, r, h);
+    return fma(fma(-g, g, z), h, g);
+}
+// acos(x) for |x| < 1 (~1 ulp).  One polynomial serves both ranges, so a warp does not diverge on |x|:
+// |x| <= 1/2: acos = pi/2 -+ asin(|x|);  |x| > 1/2: acos(|x|) = 2 asin(sqrt((1-|x|)/2)), acos(-|x|) = pi - acos(|x|).
+DEVI double facos(double x)
+{
+    const double ax = fabs(x);
+    const bool big = ax > 0.5;
+    const bool neg = x < 0.0;
+    double z, sv;
+    if (big) { z = fma(ax, -0.5, 0.5); sv = fsqrt_pos(z); }       // (1-|x|)/2 is exact for |x| >= 1/2
+    else     { z = x * x; sv = ax; }
+    double p = ka[0];
+#pragma unroll
+    for (int i = 1; i < 12; ++i) p = fma(p, z, ka[i]);
+    const double r = fma(sv * z, p, sv);                            // asin(sv)
+    const double r2 = big ? r + r : r;
+    const double base = big ? (neg ? ka[12] : 0.0) : ka[13];
+    return (neg != big) ? base + r2 : base - r2;
 }
 #endif
 
@@ -249,6 +286,38 @@ DEVI int diurnal_cycle(double amp, double tmean, double &above, double &below)
     return 2;
 }
 
+#if !SEMIC_STRICT
+// The same for the fast arithmetic mode: the quotients by amp and amp*amp are multiplications by reciprocals the caller
+// provides (host constants unless bnd%amp makes amp a field), acos/sqrt are the helpers above, and `above` leaves
+// clamped at 0 (the reference clamps it two lines later, :254).  The interior sums keep the reference's unfused order
+// for the reason given above.  tmean*inv_amp is not the IEEE quotient, so |r| is kept below 1 explicitly (IEEE
+// division of |tmean| < amp cannot round to 1); likewise 1 - tmean^2/amp^2 is kept at >= 0.
+DEVI int diurnal_cycle_fast(const double amp, const double inv_amp, const double inv_amp2, const double tmean,
+                            double &above, double &below)
+{
+    if (tmean + amp < 0.0) {                        // :459
+        below = tmean;
+        above = 0.0;
+        return 0;
+    }
+    above = tmean;
+    below = 0.0;
+    if (fabs(tmean) < amp) {                        // :465
+        double r = tmean * inv_amp;
+        if (!(fabs(r) < 1.0)) r = copysign(0x1.fffffffffffffp-1, tmean);
+        const double tmp1 = facos(r);                                                                   // :455
+        const double w = __dsub_rn(1.0, __dmul_rn(__dmul_rn(tmean, tmean), inv_amp2));                 // :456
+        const double tmp2 = sqrt(dmax1(w, 0.0));
+        const double at2 = __dmul_rn(amp, tmp2);
+        above = __dadd_rn(__dadd_rn(__dmul_rn(-tmean, tmp1), at2), __dmul_rn(ka[12], tmean)) * frcp(__dsub_rn(ka[12], tmp1));   // :467
+        above = dmax1(above, 0.0);
+        below = __dsub_rn(__dmul_rn(tmean, tmp1), at2) * frcp(tmp1);                                   // :469
+        return 1;
+    }
+    return 2;
+}
+#endif
+
 // albedo_slater, surface_physics.f90:503-530
 DEVI double albedo_slater(double tsurf, const DevPar &P)
 {
@@ -309,9 +378,14 @@ struct Pt {
 template <bool GENERIC, bool ALLG, int UNR>
 DEVI void energy_substeps(double &ts, double &t2m, double &shf, double &lhf, double &subl, double &evap, double &lwu,
                           double &q_last, double &over, bool &ice_last, const double shf_c, const double lhf_c,
-                          const double rad, const double qq, const double sp, const double qmr_res, const bool gate,
+                          const double rad, const double qq, const double sp, const double qmr_res, const bool gate_in,
                           const int nsub, const DevPar &P, const semic_bnd &B, const double *tab)
 {
+    // ALLG: every lane of the warp is gated (mask == 2 or snow covered), a compile-time true removes the selects
+    const bool gate = ALLG ? true : gate_in;
+#if !SEMIC_STRICT
+    double ts_raw = ts;                                                        // tsurf of the last sub-step before the clamp
+#endif
 #pragma unroll UNR
     for (int k = 0; k < nsub; ++k) {
         if (!BND(shf)) shf = shf_c * (ts - t2m);                               // :173
@@ -336,30 +410,28 @@ DEVI void energy_substeps(double &ts, double &t2m, double &shf, double &lhf, dou
         lwu = longwave_upward(ts, kc[17]);
 #endif
         const double qsb = (((rad - lwu) - shf) - lhf) - qmr_res;              // :194
+#if SEMIC_STRICT
         over = 0.0;                                                            // :197
         if (!BND(tsurf)) {                                                     // :198
-#if SEMIC_STRICT
             ts = ts + fdiv(qsb * P.tsticsub, P.ceff);                          // :199
             if (gate && ts > c_t0) {                                           // :201-204
                 over = ts - c_t0;
                 ts = c_t0;
             }
-#else
-            ts = fma(qsb, P.sub_over_ceff, ts);
-            if (gate && ts > kc[14]) {
-                over = ts - kc[14];
-                ts = kc[14];
-            }
-#endif
         }
-        if (gate) {                                                            // :209-211 (Q1: forcing t2m is mutated)
-#if SEMIC_STRICT
-            t2m = t2m + fdiv((shf + lhf) * P.tsticsub, P.ceff);
+        if (gate) t2m = t2m + fdiv((shf + lhf) * P.tsticsub, P.ceff);          // :209-211 (Q1: forcing t2m is mutated)
 #else
-            t2m = fma(shf + lhf, P.sub_over_ceff, t2m);
-#endif
+        if (!BND(tsurf)) {
+            ts_raw = fma(qsb, P.sub_over_ceff, ts);
+            ts = (gate && ts_raw > kc[14]) ? kc[14] : ts_raw;                  // :201-204; the excess is formed after the loop
         }
+        if (gate) t2m = fma(shf + lhf, P.sub_over_ceff, t2m);
+#endif
     }
+#if !SEMIC_STRICT
+    // only the last sub-step's excess survives (:197, Q2)
+    if (nsub > 0) over = (!BND(tsurf) && gate && ts_raw > kc[14]) ? ts_raw - kc[14] : 0.0;
+#endif
 }
 
 
@@ -439,7 +511,13 @@ DEVI unsigned point_day(Pt &s, const double *row, const long long T, const DevPa
         const double tmean = fma(qmr, P.tstic_over_ceff, ts - kc[14]);
 #endif
         double above, below;
+#if SEMIC_STRICT
         const int dbr = diurnal_cycle(amp, tmean, above, below);
+#else
+        const double inv_amp = BND(amp) ? frcp(amp) : P.inv_amp;
+        const double inv_amp2 = BND(amp) ? frcp(amp * amp) : P.inv_amp2;
+        const int dbr = diurnal_cycle_fast(amp, inv_amp, inv_amp2, tmean, above, below);
+#endif
         if (WANT_BRANCH) { branch |= (dbr == 1 ? SEMIC_B_DIURNAL_LO : (dbr == 2 ? SEMIC_B_DIURNAL_HI : 0)); }
         qmr = 0.0;                                                                 // :250
 
@@ -449,7 +527,7 @@ DEVI unsigned point_day(Pt &s, const double *row, const long long T, const DevPa
             qmelt = dmax1(0.0, fdiv(above * P.ceff, P.tstic));
             qcold = dmax1(0.0, fdiv(fabs(below) * P.ceff, P.tstic));
 #else
-            qmelt = dmax1(0.0, above * P.ceff_over_tstic);
+            qmelt = above * P.ceff_over_tstic;                    // above >= 0 on return from diurnal_cycle_fast
             qcold = fabs(below) * P.ceff_over_tstic;              // dmax1(0,|x|) == |x| for every x
 #endif
         }
@@ -484,7 +562,11 @@ DEVI unsigned point_day(Pt &s, const double *row, const long long T, const DevPa
             refr = qcold * P.inv_rhow_clm;
 #endif
             refrozen_rain = dmin1(refr, rf);                                        // :287
+#if SEMIC_STRICT
             refrozen_snow = dmax1(refr - refrozen_rain, 0.0);                       // :289
+#else
+            refrozen_snow = refr - refrozen_rain;           // refrozen_rain = min(refr, rf) <= refr: the max(.,0) of :289 is the identity
+#endif
             refrozen_snow = dmin1(refrozen_snow, melted_snow);                      // :291
             refrozen_rain = P.rcrit * dmin1(hs_rate, refrozen_rain);                // :293
             refrozen_snow = P.rcrit * dmin1(hs_rate, refrozen_snow);                // :294
@@ -529,8 +611,15 @@ DEVI unsigned point_day(Pt &s, const double *row, const long long T, const DevPa
 #if SEMIC_STRICT
             const double f_alb = 1.0 - fexp(fdiv(-hsnow, P.hcrit_eps));            // :338
 #else
-            // hcrit -> 0 makes the argument huge: exp(-700) is already 0 next to 1
-            const double f_alb = 1.0 - fexp_t(dmax1(-700.0, -hsnow * P.inv_hcrit_eps), tab);
+            // exact shortcut: exp(-x) < 2^-54 for x > 37.43, so 1 - exp(-x) rounds to 1 (taken when the whole warp is
+            // under deep snow).  hsnow <= hsmax here; only a tiny hcrit (falb_clamp) can push the argument out of
+            // fexp_t's range, and exp(-700) is already 0 next to 1.
+            double f_alb = 1.0;
+            double xs = hsnow * P.inv_hcrit_eps;
+            if (!__all_sync(__activemask(), xs > 38.0)) {
+                if (P.falb_clamp) xs = dmax1(-700.0, dmin1(xs, 700.0));
+                f_alb = 1.0 - fexp_t(-xs, tab);
+            }
 #endif
             const int scheme = (SCHEME == SCHEME_RUNTIME) ? P.scheme : SCHEME;
             if (scheme == SCHEME_SLATER)      alb_snow = albedo_slater(ts, P);     // :340-341
