@@ -439,7 +439,7 @@ DEVI void energy_substeps(double &ts, double &t2m, double &shf, double &lhf, dou
 // memory in k_ensemble): variable v is row[v*T].  Values are read where they are first needed (LDS
 // is cheap, registers across the sub-step loop are not); `swd_out` returns the day's shortwave for
 // the swnet diagnostic.
-template <int SCHEME, bool GENERIC, bool WANT_BRANCH, int UNR = 2>
+template <int SCHEME, bool GENERIC, bool WANT_BRANCH, int UNR = 2, int NK = 0>
 DEVI unsigned point_day(Pt &s, const double *row, const long long T, const DevPar &P, const semic_bnd &B,
                         const int eb_steps, const int do_mb, double &swd_out, const double *tab)
 {
@@ -464,7 +464,7 @@ DEVI unsigned point_day(Pt &s, const double *row, const long long T, const DevPa
         const double qq = row[SEMIC_V_QQ * T], sp = row[SEMIC_V_SP * T];
         double q_last = 0.0, over = 0.0;
         bool ice_last = false;
-        const int nsub = GENERIC ? eb_steps : P.n_ksub;
+        const int nsub = GENERIC ? eb_steps : (NK > 0 ? NK : P.n_ksub);        // NK: n_ksub known at compile time
         const bool any = nsub > 0;
         // gated points never exceed t0 (:201-204), which removes the ei/ew constant selects (see latent_q); taken when
         // every active lane of the warp is gated, e.g. the interior of an ice sheet
@@ -916,7 +916,7 @@ DEVI bool elect_one()
     return pred != 0;
 }
 
-template <int SCHEME, int WPC, int UNR>
+template <int SCHEME, int WPC, int UNR, int NK>
 __global__ void __launch_bounds__(WPC * 32, 1) k_run_lean(const __grid_constant__ RunArgs a)
 {
     using SM = RunSmem<false, WPC>;
@@ -948,12 +948,14 @@ __global__ void __launch_bounds__(WPC * 32, 1) k_run_lean(const __grid_constant_
     const long long o_day = ntl * OBLK;
     const int ndays = a.ndays;
     __builtin_assume(a.P.n_ksub >= 1);                           // guaranteed by the launcher (n_ksub < 1 runs k_run)
-    const int ostart = (a.out != nullptr) ? a.out_start : ndays;
+    int ostart = (a.out != nullptr) ? a.out_start : ndays;       // first day that is written
+    asm volatile("" : "+r"(ostart));                             // keep it in a register instead of re-deriving it daily
     uint32_t stage = 0, phase = 0;
 
     for (long long tile = (long long)blockIdx.x * WPC + warp; tile < ntiles; tile += nwarps) {
         const double *ftile = a.forcing + tile * FBLK;
-        int fd = a.f_day0 % a.f_nwin;
+        const double *fend = ftile + (long long)a.f_nwin * f_day;
+        const double *fsrc = ftile + (long long)(a.f_day0 % a.f_nwin) * f_day;   // next forcing day to fetch
         int d_issue = 0;
         {
             uint32_t s = stage;
@@ -961,14 +963,17 @@ __global__ void __launch_bounds__(WPC * 32, 1) k_run_lean(const __grid_constant_
             for (; d_issue < npre; ++d_issue) {
                 if (elect_one()) {
                     mbar_expect_tx(bar_u + 8u * s, SB);
-                    tma_load_1d(ring_u + s * SB, ftile + (long long)fd * f_day, SB, bar_u + 8u * s);
+                    tma_load_1d(ring_u + s * SB, fsrc, SB, bar_u + 8u * s);
                 }
-                if (++fd == a.f_nwin) fd = 0;
+                fsrc += f_day;
+                if (fsrc == fend) fsrc = ftile;
                 if (++s == NST) s = 0;
             }
         }
 
         const long long i = tile * kTile + lane;
+        int dlast = (i < a.nx) ? ndays - 1 : -1;                 // the day whose full state this lane stores
+        asm volatile("" : "+r"(dlast));
         Pt s;
         {
             const double *S = a.slab + i;                        // the slab has ld >= ntiles*32 columns
@@ -986,11 +991,11 @@ __global__ void __launch_bounds__(WPC * 32, 1) k_run_lean(const __grid_constant_
         double *oday = a.out + tile * OBLK + lane;
         int oslot = 0;
 
-        auto one_day = [&](const int d) {
+        for (int d = 0; d < ndays; ++d) {
             mbar_wait(bar_u + 8u * stage, phase);
             const double *row = ring + (size_t)stage * (SB / sizeof(double));
             double swd;
-            point_day<SCHEME, false, false, UNR>(s, row, kTile, a.P, a.B, 0, 1, swd, tab);
+            point_day<SCHEME, false, false, UNR, NK>(s, row, kTile, a.P, a.B, 0, 1, swd, tab);
             if (d >= ostart) {                                   // example.f90:117-122
                 oday[SEMIC_O_STT * kTile]   = s.tsurf;
                 oday[SEMIC_O_ALB * kTile]   = s.alb;
@@ -1003,7 +1008,7 @@ __global__ void __launch_bounds__(WPC * 32, 1) k_run_lean(const __grid_constant_
                 oday += o_day;
                 if (++oslot == a.o_nring) { oslot = 0; oday -= (long long)a.o_nring * o_day; }
             }
-            if (d == ndays - 1 && i < a.nx) {   // final state: all 23 non-forcing fields, as after the reference's last call
+            if (d == dlast) {                   // final state: all 23 non-forcing fields, as after the reference's last call
                 double *S = a.slab + i;
                 S[SEMIC_F_T2M * ld] = s.t2m;
                 S[SEMIC_F_TSURF * ld] = s.tsurf;
@@ -1034,15 +1039,14 @@ __global__ void __launch_bounds__(WPC * 32, 1) k_run_lean(const __grid_constant_
             if (d_issue < ndays) {
                 if (elect_one()) {
                     mbar_expect_tx(bar_u + 8u * stage, SB);
-                    tma_load_1d(ring_u + stage * SB, ftile + (long long)fd * f_day, SB, bar_u + 8u * stage);
+                    tma_load_1d(ring_u + stage * SB, fsrc, SB, bar_u + 8u * stage);
                 }
                 ++d_issue;
-                if (++fd == a.f_nwin) fd = 0;
+                fsrc += f_day;
+                if (fsrc == fend) fsrc = ftile;
             }
             if (++stage == NST) { stage = 0; phase ^= 1u; }
-        };
-
-        for (int d = 0; d < ndays; ++d) one_day(d);
+        }
     }
 }
 

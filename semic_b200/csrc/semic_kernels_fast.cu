@@ -44,8 +44,7 @@ cudaError_t launch_run_fast(const RunArgs &a, bool generic, cudaStream_t st, int
     const int shape = e ? atoi(e) * 10 + (strchr(e, 'x') ? atoi(strchr(e, 'x') + 1) : 0) : 240;
     const bool lean_ok = a.f_tiled && a.ndays >= 1 && a.P.n_ksub >= 1 && (a.out == nullptr || a.o_nvar == SEMIC_NOUT);
     if (lean_ok && (shape == 240 || shape == 200)) {                         // "24x0" / "20x0": k_run_lean
-        if (shape == 200) return a.P.n_ksub >= 8 ? fast_mode::launch_lean<20, 4>(a, st) : fast_mode::launch_lean<20, 2>(a, st);
-        return a.P.n_ksub >= 8 ? fast_mode::launch_lean<24, 4>(a, st) : fast_mode::launch_lean<24, 2>(a, st);
+        return shape == 200 ? fast_mode::launch_lean<20>(a, st) : fast_mode::launch_lean<24>(a, st);
     }
     switch (shape) {
         case 82:  return fast_mode::launch_scheme<false, 2, 8>(a, st);       // 16 warps, <=128 regs

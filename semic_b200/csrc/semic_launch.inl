@@ -42,10 +42,10 @@ static cudaError_t launch_scheme(const RunArgs &a, cudaStream_t st)
 
 #if !SEMIC_STRICT
 // k_run_lean: the plain (no boundary flag) tiled-forcing run with 8 daily rows, n_ksub >= 1
-template <int SCHEME, int WPC, int UNR>
+template <int SCHEME, int WPC, int UNR, int NK>
 static cudaError_t launch_lean_one(const RunArgs &a, cudaStream_t st)
 {
-    auto kern = k_run_lean<SCHEME, WPC, UNR>;
+    auto kern = k_run_lean<SCHEME, WPC, UNR, NK>;
     constexpr size_t smem = RunSmem<false, WPC>::bytes;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
@@ -61,16 +61,26 @@ static cudaError_t launch_lean_one(const RunArgs &a, cudaStream_t st)
     return cudaGetLastError();
 }
 
-template <int WPC, int UNR>
-static cudaError_t launch_lean(const RunArgs &a, cudaStream_t st)
+template <int WPC, int UNR, int NK>
+static cudaError_t launch_lean_nk(const RunArgs &a, cudaStream_t st)
 {
     switch (a.P.scheme) {
-        case SCHEME_NONE:   return launch_lean_one<SCHEME_NONE, WPC, UNR>(a, st);
-        case SCHEME_SLATER: return launch_lean_one<SCHEME_SLATER, WPC, UNR>(a, st);
-        case SCHEME_DENBY:  return launch_lean_one<SCHEME_DENBY, WPC, UNR>(a, st);
-        case SCHEME_ISBA:   return launch_lean_one<SCHEME_ISBA, WPC, UNR>(a, st);
-        case SCHEME_ALEX:   return launch_lean_one<SCHEME_ALEX, WPC, UNR>(a, st);
-        default:            return launch_lean_one<SCHEME_UNKNOWN, WPC, UNR>(a, st);
+        case SCHEME_NONE:   return launch_lean_one<SCHEME_NONE, WPC, UNR, NK>(a, st);
+        case SCHEME_SLATER: return launch_lean_one<SCHEME_SLATER, WPC, UNR, NK>(a, st);
+        case SCHEME_DENBY:  return launch_lean_one<SCHEME_DENBY, WPC, UNR, NK>(a, st);
+        case SCHEME_ISBA:   return launch_lean_one<SCHEME_ISBA, WPC, UNR, NK>(a, st);
+        case SCHEME_ALEX:   return launch_lean_one<SCHEME_ALEX, WPC, UNR, NK>(a, st);
+        default:            return launch_lean_one<SCHEME_UNKNOWN, WPC, UNR, NK>(a, st);
     }
+}
+
+// n_ksub = 3 (every shipped namelist: example.namelist:30, optimization.namelist, tools.py:31) is a compile-time
+// constant of its own instantiation: the three sub-steps share one set of constant loads
+template <int WPC>
+static cudaError_t launch_lean(const RunArgs &a, cudaStream_t st)
+{
+    if (a.P.n_ksub == 3) return launch_lean_nk<WPC, 3, 3>(a, st);
+    if (a.P.n_ksub >= 8) return launch_lean_nk<WPC, 4, 0>(a, st);
+    return launch_lean_nk<WPC, 2, 0>(a, st);
 }
 #endif
