@@ -16,7 +16,7 @@ enum { SCHEME_NONE = 0, SCHEME_SLATER = 1, SCHEME_DENBY = 2, SCHEME_ISBA = 3, SC
 // Geometry of the persistent kernel: every warp owns tiles of 32 consecutive points and a private
 // shared-memory ring of kStages days fed by its own TMA bulk copies (no producer warp, no cross-warp coupling).
 constexpr int kTile          = 32;                       // points per warp tile = lanes
-constexpr int kStages        = 4;                        // days of forcing in flight per warp
+constexpr int kStages        = 3;                        // days of forcing in flight per warp
 constexpr int kLdAlign       = 1024;                     // leading dimensions: multiples of this (=> whole tiles, 16-byte rows)
 constexpr int kForcingRows   = 9;
 constexpr int kExtRows       = 5;                        // tsurf alb smb melt acc overrides

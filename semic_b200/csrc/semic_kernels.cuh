@@ -49,7 +49,7 @@ constexpr double c_hsmax = 5.0;
 // ------------------------------------------------------------------------------------------------
 // Literal doubles of the hot loop live in the constant bank so that they are direct c[3][..]
 // operands of DFMA/DMUL; as immediates ptxas re-materialises each one with two UMOVs per use.
-__device__ __constant__ double kc[24] = {
+__device__ __constant__ double kc[26] = {
     6755399441055744.0,           //  0  1.5*2^52
     1.4426950408889634,           //  1  log2(e)
     -6.93147180369123816490e-01,  //  2  -ln2 hi
@@ -70,34 +70,22 @@ __device__ __constant__ double kc[24] = {
     5.67e-8,                      // 17  sigm
     22.46, 272.62,                // 18 19  ei_sat a, b
     17.62, 243.12,                // 20 21  ew_sat a, b
-    2.83e6, 2.5e6                 // 22 23  cls, clv
+    2.83e6, 2.5e6,                // 22 23  cls, clv
+    -22.46, -17.62                // 24 25  -a of ei_sat, ew_sat
 };
 // dmax1/dmin1 as compare-select (3 instructions; IEEE fmax/fmin costs 6 on sm_100a, there is no DMNMX).
 // Identical to fmax/fmin on ordered operands; with a NaN operand the second argument is returned.
 DEVI double dmax1(double a, double b) { return a > b ? a : b; }
 DEVI double dmin1(double a, double b) { return a < b ? a : b; }
-// 2^(j/64), j = 0..63 (correctly rounded), staged into shared memory by the kernels that use fexp_t
-__device__ __constant__ double c_exp2_tab[64] = {
-    1, 1.0108892860517005, 1.0218971486541166, 1.0330248790212284,
-    1.0442737824274138, 1.0556451783605572, 1.0671404006768237, 1.0787607977571199,
-    1.0905077326652577, 1.1023825833078409, 1.1143867425958924, 1.1265216186082418,
-    1.1387886347566916, 1.1511892299529827, 1.1637248587775775, 1.1763969916502812,
-    1.189207115002721, 1.2021567314527031, 1.215247359980469, 1.22848053610687,
-    1.241857812073484, 1.2553807570246911, 1.2690509571917332, 1.2828700160787783,
-    1.2968395546510096, 1.3109612115247644, 1.3252366431597413, 1.3396675240533029,
-    1.3542555469368927, 1.3690024229745905, 1.383909881963832, 1.3989796725383112,
-    1.4142135623730951, 1.42961333839197, 1.4451808069770467, 1.460917794180647,
-    1.4768261459394993, 1.4929077282912648, 1.5091644275934228, 1.5255981507445384,
-    1.5422108254079407, 1.5590044002378369, 1.5759808451078865, 1.593142151342267,
-    1.6104903319492543, 1.6280274218573478, 1.6457554781539649, 1.6636765803267364,
-    1.681792830507429, 1.7001063537185235, 1.7186192981224779, 1.7373338352737062,
-    1.7562521603732995, 1.7753764925265212, 1.7947090750031072, 1.8142521755003989,
-    1.8340080864093424, 1.8539791250833855, 1.8741676341103, 1.8945759815869656,
-    1.9152065613971474, 1.9360617934922943, 1.9571441241754002, 1.9784560263879509
-};
-// constants of the table-driven exp: 64/ln2, 1.5*2^52, -(ln2/64) hi (low 20 mantissa bits zero) and lo, Taylor 1/2..1/120
-__device__ __constant__ double kt[8] = {92.33248261689366, 6755399441055744.0, -0.010830424695086549, -1.162596423439437e-12,
-                                        0.5, 1.6666666666666666e-01, 4.1666666666666664e-02, 8.3333333333333332e-03};
+// 2^(j/2048), j = 0..2047: filled once per device by the host (exp2l, rounded to double), staged into shared memory by
+// the kernels that use fexp_t
+constexpr int kExpTab = 2048;
+#if !SEMIC_STRICT
+__device__ double g_exp2_tab[kExpTab];
+#endif
+// constants of the table-driven exp: 2048/ln2, 1.5*2^52, -(ln2/2048) hi (low 22 mantissa bits zero) and lo, Taylor 1/2, 1/6
+__device__ __constant__ double kt[6] = {2954.639443740597, 6755399441055744.0, -0.0003384507715509244, -2.0686139481490644e-13,
+                                        0.5, 0.16666666666666666};
 #if SEMIC_STRICT
 DEVI double fdiv(double n, double d) { return n / d; }    // CUDA double division is IEEE round-to-nearest
 DEVI double fexp(double x) { return exp(x); }
@@ -141,9 +129,9 @@ DEVI double fexp(double x)
     double p = fma(q2, r8, h0);
     return __hiloint2double(__double2hiint(p) + (k << 20), __double2loint(p));
 }
-// Table-driven exp for the hot loop: exp(x) = 2^k * 2^(j/64) * p(r), n = rint(x*64/ln2) = 64k + j,
-// |r| <= ln2/128, p = degree-5 Taylor (truncation 3.4e-17).  11 FP64 operations instead of 20 and 8 constants
-// instead of 14; the table lives in shared memory (LDS with a lane-varying index).  |x| < 700, no specials.
+// Table-driven exp for the hot loop: exp(x) = 2^k * 2^(j/2048) * p(r), n = rint(x*2048/ln2) = 2048k + j,
+// |r| <= ln2/4096, p = degree-3 Taylor (truncation r^4/24 <= 3.4e-17).  9 FP64 operations; the table lives in shared
+// memory (LDS with a lane-varying index).  |x| < 700, no specials.
 DEVI double fexp_t(double x, const double *tab)
 {
     const double t = fma(x, kt[0], kt[1]);
@@ -154,10 +142,8 @@ DEVI double fexp_t(double x, const double *tab)
     const double r2 = r * r;
     const double p01 = r + 1.0;
     const double p23 = fma(kt[5], r, kt[4]);
-    const double p45 = fma(kt[7], r, kt[6]);
-    const double q = fma(p45, r2, p23);
-    const double p = fma(q, r2, p01) * tab[n & 63];
-    return __hiloint2double(__double2hiint(p) + ((n >> 6) << 20), __double2loint(p));
+    const double p = fma(p23, r2, p01) * tab[n & (kExpTab - 1)];
+    return __hiloint2double(__double2hiint(p) + ((n >> 11) << 20), __double2loint(p));
 }
 // asin(s) = s + s*z*R(z), z = s*s <= 1/4: degree-11 interpolant of R at the Chebyshev nodes of [0, 1/4]
 // (relative error of asin 5.6e-17 before rounding); coefficients highest degree first
@@ -226,25 +212,28 @@ DEVI double esat(double ts, bool ice)
 }
 
 // latent_heat_flux, surface_physics.f90:393-430; returns q = subl (ice) or evap (water) in kg/(s m2)
-// ALLG: the caller guarantees ts <= t0 (the point is gated, :201): at ts == t0 the argument a*x/(b+x) is 0 for either
-// pair (a,b), so the ice constants serve both branches bit for bit and the two selects disappear.
-template <bool ALLG = false>
-DEVI double latent_q(double ts, double wind_clh_rho, double shum, double sp, bool ice, const double *tab)
-{
-    (void)tab;
 #if SEMIC_STRICT
+DEVI double latent_q(double ts, double wind_clh_rho, double shum, double sp, bool ice)
+{
     const double es = esat(ts, ice);
     const double shum_sat = fdiv(es * c_eps, (es * (c_eps - 1.0)) + sp);
-#else
-    // 611.2 folded into the two eps factors: es*eps/(es*(eps-1)+sp)
-    const double a = (ALLG || ice) ? kc[18] : kc[20];
-    const double b = (ALLG || ice) ? kc[19] : kc[21];
-    const double x = ts - kc[14];
-    const double e = fexp_t((a * x) * frcp(b + x), tab);
-    const double shum_sat = (e * kc[15]) * frcp(fma(e, kc[16], sp));
-#endif
     return wind_clh_rho * (shum_sat - shum);
 }
+#else
+// Fast form.  With em = exp(-a x/(b+x)) = 611.2/es:  es*eps/(es*(eps-1)+sp) = 611.2*eps / (611.2*(eps-1) + sp*em), so
+// q = A/(611.2*(eps-1) + sp*em) - Bq with the day constants A = wind_clh_rho*611.2*eps, Bq = wind_clh_rho*shum.
+// ALLG: the caller guarantees ts <= t0 (the point is gated, :201): at ts == t0 the argument a*x/(b+x) is 0 for either
+// pair (a,b), so the ice constants serve both branches bit for bit and the two selects disappear.
+template <bool ALLG>
+DEVI double latent_q(double ts, double A, double Bq, double sp, bool ice, const double *tab)
+{
+    const double na = (ALLG || ice) ? kc[24] : kc[25];
+    const double b = (ALLG || ice) ? kc[19] : kc[21];
+    const double x = ts - kc[14];
+    const double em = fexp_t((na * x) * frcp(b + x), tab);
+    return fma(frcp(fma(sp, em, kc[16])), A, -Bq);
+}
+#endif
 
 // longwave_upward, surface_physics.f90:434-438
 DEVI double longwave_upward(double ts, double sigma)
@@ -385,6 +374,8 @@ DEVI void energy_substeps(double &ts, double &t2m, double &shf, double &lhf, dou
     const bool gate = ALLG ? true : gate_in;
 #if !SEMIC_STRICT
     double ts_raw = ts;                                                        // tsurf of the last sub-step before the clamp
+    const double lat_a = lhf_c * kc[15], lat_b = lhf_c * qq;                   // day constants of latent_q
+    const double radq = rad - qmr_res;                                         // :194 with the day-constant terms first
 #endif
 #pragma unroll UNR
     for (int k = 0; k < nsub; ++k) {
@@ -392,11 +383,11 @@ DEVI void energy_substeps(double &ts, double &t2m, double &shf, double &lhf, dou
         if (!BND(lhf)) {                                                       // :179-185
 #if SEMIC_STRICT
             const bool ice = ts < c_t0;                                        // :415
-            const double q = latent_q<false>(ts, lhf_c, qq, sp, ice, tab);
+            const double q = latent_q(ts, lhf_c, qq, sp, ice);
             lhf = q * (ice ? c_cls : c_clv);                                   // :421,:428
 #else
             const bool ice = ts < kc[14];
-            const double q = latent_q<ALLG>(ts, lhf_c, qq, sp, ice, tab);
+            const double q = latent_q<ALLG>(ts, lat_a, lat_b, sp, ice, tab);
             lhf = q * (ice ? kc[22] : kc[23]);
 #endif
             q_last = q;
@@ -409,8 +400,8 @@ DEVI void energy_substeps(double &ts, double &t2m, double &shf, double &lhf, dou
 #else
         lwu = longwave_upward(ts, kc[17]);
 #endif
-        const double qsb = (((rad - lwu) - shf) - lhf) - qmr_res;              // :194
 #if SEMIC_STRICT
+        const double qsb = (((rad - lwu) - shf) - lhf) - qmr_res;              // :194
         over = 0.0;                                                            // :197
         if (!BND(tsurf)) {                                                     // :198
             ts = ts + fdiv(qsb * P.tsticsub, P.ceff);                          // :199
@@ -421,6 +412,7 @@ DEVI void energy_substeps(double &ts, double &t2m, double &shf, double &lhf, dou
         }
         if (gate) t2m = t2m + fdiv((shf + lhf) * P.tsticsub, P.ceff);          // :209-211 (Q1: forcing t2m is mutated)
 #else
+        const double qsb = ((radq - lwu) - shf) - lhf;
         if (!BND(tsurf)) {
             ts_raw = fma(qsb, P.sub_over_ceff, ts);
             ts = (gate && ts_raw > kc[14]) ? kc[14] : ts_raw;                  // :201-204; the excess is formed after the loop
@@ -695,7 +687,7 @@ struct RunSmem {
     static constexpr size_t stage_bytes = (size_t)ROWS * kTile * sizeof(double);          // 2304 B (3584 B generic)
     static constexpr size_t ring_bytes = stage_bytes * STAGES * WPC;
     static constexpr size_t bar_bytes = (size_t)WPC * STAGES * sizeof(uint64_t);
-    static constexpr size_t bytes = ring_bytes + bar_bytes + 64 * sizeof(double);          // rings, barriers, exp table
+    static constexpr size_t bytes = ring_bytes + bar_bytes + (SEMIC_STRICT ? 0 : kExpTab) * sizeof(double);   // rings, barriers, exp table
 };
 
 // validation-layout rows that feed the overrides tsurf, alb, smb, melt, acc (example.f90:103-107)
@@ -741,7 +733,9 @@ __global__ void __launch_bounds__(WPC * 32, MINB) k_run(const __grid_constant__ 
         for (int s = 0; s < NST; ++s) mbar_init(bar_u + 8u * s, 1);
         mbar_fence_init();
     }
-    if (threadIdx.x < 64) tab[threadIdx.x] = c_exp2_tab[threadIdx.x];
+#if !SEMIC_STRICT
+    for (int j = threadIdx.x; j < kExpTab; j += WPC * 32) tab[j] = g_exp2_tab[j];
+#endif
     __syncthreads();
 
     bool ext_on[kExtRows] = {false, false, false, false, false};
@@ -937,7 +931,7 @@ __global__ void __launch_bounds__(WPC * 32, 1) k_run_lean(const __grid_constant_
         for (int s = 0; s < NST; ++s) mbar_init(bar_u + 8u * s, 1);
         mbar_fence_init();
     }
-    if (threadIdx.x < 64) tab[threadIdx.x] = c_exp2_tab[threadIdx.x];
+    for (int j = threadIdx.x; j < kExpTab; j += WPC * 32) tab[j] = g_exp2_tab[j];
     __syncthreads();
 
     const long long ld = a.ld;
@@ -1064,8 +1058,8 @@ constexpr int kEnsParticles = 8;
 __global__ void __launch_bounds__(32 * kEnsParticles) k_ensemble(const EnsArgs a, const int ngroups)
 {
     __shared__ DevPar s_par[kEnsParticles];
-    __shared__ double tab[64];
-    if (threadIdx.x < 64) tab[threadIdx.x] = c_exp2_tab[threadIdx.x];
+    __shared__ double tab[kExpTab];
+    for (int j = threadIdx.x; j < kExpTab; j += 32 * kEnsParticles) tab[j] = g_exp2_tab[j];
     const int tile = blockIdx.x / ngroups;
     const int group = blockIdx.x % ngroups;
     const int lane = threadIdx.x & 31;

@@ -2,8 +2,10 @@
 // MUFU-seeded division, custom exp.  Parity bar: 1e-10 relative per variable after one year.
 #define SEMIC_STRICT 0
 #define SEMIC_MODE_NS fast_mode
+#include <cmath>
 #include <cstdlib>
 #include <cstring>
+#include <mutex>
 #include "semic_kernels.cuh"
 
 namespace semic {
@@ -35,9 +37,29 @@ __global__ void k_elementals(int which, const double *in0, const double *in1, co
 }
 }  // namespace fast_mode
 
+// g_exp2_tab of the current device: 2^(j/2048) from the host's long-double exp2 (x87: 64-bit mantissa), rounded to double
+static cudaError_t ensure_exp_table()
+{
+    constexpr int kMaxDev = 64;
+    static std::mutex mu;
+    static bool done[kMaxDev] = {};
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return e;
+    if (dev < 0 || dev >= kMaxDev) return cudaErrorInvalidDevice;
+    std::lock_guard<std::mutex> lock(mu);
+    if (done[dev]) return cudaSuccess;
+    static double host_tab[fast_mode::kExpTab];
+    for (int j = 0; j < fast_mode::kExpTab; ++j) host_tab[j] = (double)exp2l((long double)j / (long double)fast_mode::kExpTab);
+    e = cudaMemcpyToSymbol(fast_mode::g_exp2_tab, host_tab, sizeof host_tab);     // synchronous: ordered before any later launch
+    if (e == cudaSuccess) done[dev] = true;
+    return e;
+}
+
 cudaError_t launch_run_fast(const RunArgs &a, bool generic, cudaStream_t st, int *launches)
 {
     if (launches) ++*launches;
+    if (cudaError_t e = ensure_exp_table()) return e;
     if (generic) return fast_mode::launch_scheme<true, 1, 8>(a, st);
     // tuning knob SEMIC_SHAPE = "<warps per CTA>x<CTAs per SM>" (default 8x3: 24 warps per SM at <= 80 registers)
     const char *e = getenv("SEMIC_SHAPE");
@@ -67,6 +89,7 @@ cudaError_t launch_vali_invvar(const EnsArgs &a, double *inv_var, cudaStream_t s
 cudaError_t launch_ensemble_fast(const EnsArgs &a, double *sumsq_dev, cudaStream_t st)
 {
     if (a.nx <= 0 || a.npar <= 0) return cudaSuccess;
+    if (cudaError_t e = ensure_exp_table()) return e;
     const int ngroups = (a.npar + fast_mode::kEnsParticles - 1) / fast_mode::kEnsParticles;
     const long long nblocks = (long long)a.ntiles * ngroups;
     if (nblocks > 0x7fffffffLL) return cudaErrorInvalidValue;
