@@ -96,7 +96,6 @@ static DevPar make_devpar(const semic_par *par)
     P.inv_hcrit_eps = 1.0 / P.hcrit_eps;
     P.inv_amp = 1.0 / par->amp;
     P.inv_amp2 = 1.0 / (par->amp * par->amp);
-    P.falb_clamp = !(5.0 * P.inv_hcrit_eps < 700.0);
     P.inv_mcrit = 1.0 / par->mcrit;
     P.isba_new = par->tstic / P.isba_wcr * P.smax_m_smin;
     P.frz_rhow_clm = P.one_m_frz * rhow * clm;

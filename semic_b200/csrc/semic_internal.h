@@ -52,8 +52,6 @@ struct DevPar {
     double frz_rhow_clm;     // (1-f_rz)*rhow*clm
     int    n_ksub;
     int    scheme;
-    int    falb_clamp;       // hsmax/(hcrit+epsil) >= 700: clamp the argument of the f_alb exponential
-    int    pad_;
 };
 
 // Series (forcing, validation, daily output) are stored TILE-INTERLEAVED in HBM:

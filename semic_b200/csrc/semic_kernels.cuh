@@ -310,12 +310,15 @@ DEVI int diurnal_cycle_fast(const double amp, const double inv_amp, const double
 // albedo_slater, surface_physics.f90:503-530
 DEVI double albedo_slater(double tsurf, const DevPar &P)
 {
+#if SEMIC_STRICT
     double tm = 0.0;
     if (tsurf >= P.tmin && tsurf <= P.tmax) tm = P.slater_f * (tsurf - P.tmin);
     if (tsurf > c_t0) tm = 1.0;
-#if SEMIC_STRICT
     return P.alb_smax - (P.smax_m_smin * pow(tm, 3.0));
 #else
+    const bool in = (tsurf >= P.tmin) & (tsurf <= P.tmax);
+    double tm = in ? P.slater_f * (tsurf - P.tmin) : 0.0;
+    tm = (tsurf > kc[14]) ? 1.0 : tm;
     return fma(-P.smax_m_smin, tm * tm * tm, P.alb_smax);
 #endif
 }
@@ -514,15 +517,19 @@ DEVI unsigned point_day(Pt &s, const double *row, const long long T, const DevPa
         qmr = 0.0;                                                                 // :250
 
         double qmelt = 0.0, qcold = 0.0;
-        if (mask >= 1) {                                                           // :252-261
+        if (SEMIC_STRICT && mask >= 1) {                                           // :252-261
 #if SEMIC_STRICT
             qmelt = dmax1(0.0, fdiv(above * P.ceff, P.tstic));
             qcold = dmax1(0.0, fdiv(fabs(below) * P.ceff, P.tstic));
-#else
-            qmelt = above * P.ceff_over_tstic;                    // above >= 0 on return from diurnal_cycle_fast
-            qcold = fabs(below) * P.ceff_over_tstic;              // dmax1(0,|x|) == |x| for every x
 #endif
         }
+#if !SEMIC_STRICT
+        {   // above >= 0 on return from diurnal_cycle_fast and dmax1(0,|x|) == |x|; finite values times 0 are the :252-261 zeros
+            const double c_mask = (mask >= 1) ? P.ceff_over_tstic : 0.0;
+            qmelt = above * c_mask;
+            qcold = fabs(below) * c_mask;
+        }
+#endif
 #if SEMIC_STRICT
         if (!BND(melt)) melt = fdiv(qmelt, P.rhow_clm);                            // :266
         const double hs_rate = fdiv(hsnow, P.tstic);
@@ -538,12 +545,8 @@ DEVI unsigned point_day(Pt &s, const double *row, const long long T, const DevPa
         melted_snow = dmin1(melt, hs_rate);                                         // :269
         melted_ice  = melt - melted_snow;                                          // :270
         if (!BND(melt)) {                                                          // :272-280
-            if (mask == 2) {
-                melt = melted_snow + melted_ice;
-            } else {
-                melt = melted_snow;
-                melted_ice = 0.0;
-            }
+            if (mask != 2) melted_ice = 0.0;
+            melt = melted_snow + melted_ice;                                       // x + 0 == x: the land/ocean branch of :277
         }
 
         double refrozen_rain = 0.0, refrozen_snow = 0.0;                           // Q5: defined as 0 under bnd%refr
@@ -574,11 +577,14 @@ DEVI unsigned point_day(Pt &s, const double *row, const long long T, const DevPa
         if (!BND(acc)) acc = (sf - subl) + refr;                                   // :307
         if (!BND(smb)) smb_snow = ((sf - subl) - melted_snow) + refrozen_snow;     // :312
 
-        if (mask == 0) hsnow = 0.0;                                                // :315-320
 #if SEMIC_STRICT
+        if (mask == 0) hsnow = 0.0;                                                // :315-320
         else hsnow = dmax1(0.0, hsnow + (smb_snow * P.tstic));
 #else
-        else hsnow = dmax1(0.0, __dadd_rn(hsnow, __dmul_rn(smb_snow, P.tstic)));      // unfused, see hs_rate
+        {
+            const double hs_new = __dadd_rn(hsnow, __dmul_rn(smb_snow, P.tstic));  // unfused, see hs_rate
+            hsnow = ((hs_new > 0.0) & (mask != 0)) ? hs_new : 0.0;                 // :315-320 with one select
+        }
 #endif
         const double snow_to_ice = dmax1(0.0, hsnow - c_hsmax);                     // :323
         hsnow = hsnow - snow_to_ice;                                               // :324
@@ -604,12 +610,11 @@ DEVI unsigned point_day(Pt &s, const double *row, const long long T, const DevPa
             const double f_alb = 1.0 - fexp(fdiv(-hsnow, P.hcrit_eps));            // :338
 #else
             // exact shortcut: exp(-x) < 2^-54 for x > 37.43, so 1 - exp(-x) rounds to 1 (taken when the whole warp is
-            // under deep snow).  hsnow <= hsmax here; only a tiny hcrit (falb_clamp) can push the argument out of
-            // fexp_t's range, and exp(-700) is already 0 next to 1.
+            // under deep snow).  A tiny hcrit can push the argument out of fexp_t's range; exp(-700) is already 0 next to 1.
             double f_alb = 1.0;
             double xs = hsnow * P.inv_hcrit_eps;
             if (!__all_sync(__activemask(), xs > 38.0)) {
-                if (P.falb_clamp) xs = dmax1(-700.0, dmin1(xs, 700.0));
+                xs = dmin1(xs, 700.0);
                 f_alb = 1.0 - fexp_t(-xs, tab);
             }
 #endif
@@ -948,8 +953,8 @@ __global__ void __launch_bounds__(WPC * 32, 1) k_run_lean(const __grid_constant_
 
     for (long long tile = (long long)blockIdx.x * WPC + warp; tile < ntiles; tile += nwarps) {
         const double *ftile = a.forcing + tile * FBLK;
-        const double *fend = ftile + (long long)a.f_nwin * f_day;
-        const double *fsrc = ftile + (long long)(a.f_day0 % a.f_nwin) * f_day;   // next forcing day to fetch
+        int fd = a.f_day0 % a.f_nwin;                            // next forcing day to fetch and its address
+        const double *fsrc = ftile + (long long)fd * f_day;
         int d_issue = 0;
         {
             uint32_t s = stage;
@@ -960,7 +965,7 @@ __global__ void __launch_bounds__(WPC * 32, 1) k_run_lean(const __grid_constant_
                     tma_load_1d(ring_u + s * SB, fsrc, SB, bar_u + 8u * s);
                 }
                 fsrc += f_day;
-                if (fsrc == fend) fsrc = ftile;
+                if (++fd == a.f_nwin) { fd = 0; fsrc = ftile; }
                 if (++s == NST) s = 0;
             }
         }
@@ -1037,7 +1042,7 @@ __global__ void __launch_bounds__(WPC * 32, 1) k_run_lean(const __grid_constant_
                 }
                 ++d_issue;
                 fsrc += f_day;
-                if (fsrc == fend) fsrc = ftile;
+                if (++fd == a.f_nwin) { fd = 0; fsrc = ftile; }
             }
             if (++stage == NST) { stage = 0; phase ^= 1u; }
         }
