@@ -337,18 +337,20 @@ DEVI double albedo_denby(double melt, const DevPar &P)
 DEVI double albedo_isba(double alb, double sf, double melt, const DevPar &P)
 {
     const double alb_dry = alb - P.isba_dry;
-    const double alb_wet = ((alb - P.alb_smin) * P.isba_wet) + P.alb_smin;
 #if SEMIC_STRICT
+    const double alb_wet = ((alb - P.alb_smin) * P.isba_wet) + P.alb_smin;
     const double alb_new = fdiv(sf * P.tstic, P.isba_wcr) * P.smax_m_smin;
     double w_alb = 0.0;
     if (melt > 0.0) w_alb = 1.0 - fdiv(melt, P.mcrit);
-#else
-    const double alb_new = sf * P.isba_new;
-    double w_alb = 0.0;
-    if (melt > 0.0) w_alb = fma(-melt, P.inv_mcrit, 1.0);
-#endif
     w_alb = dmin1(1.0, dmax1(w_alb, 0.0));
     double a = (((1.0 - w_alb) * alb_dry) + (w_alb * alb_wet)) + alb_new;
+#else
+    const double alb_wet = fma(alb - P.alb_smin, P.isba_wet, P.alb_smin);
+    double w_alb = 0.0;
+    if (melt > 0.0) w_alb = fma(-melt, P.inv_mcrit, 1.0);
+    w_alb = dmin1(1.0, dmax1(w_alb, 0.0));
+    double a = fma(sf, P.isba_new, fma(w_alb, alb_wet, (1.0 - w_alb) * alb_dry));
+#endif
     return dmin1(P.alb_smax, dmax1(a, P.alb_smin));
 }
 
@@ -367,43 +369,27 @@ struct Pt {
 #define BND(x) (GENERIC && (B.x != 0))
 
 // n_ksub x energy_balance (surface_physics.f90:158-214) for one point; state in registers
+#if SEMIC_STRICT
 template <bool GENERIC, bool ALLG, int UNR>
 DEVI void energy_substeps(double &ts, double &t2m, double &shf, double &lhf, double &subl, double &evap, double &lwu,
                           double &q_last, double &over, bool &ice_last, const double shf_c, const double lhf_c,
-                          const double rad, const double qq, const double sp, const double qmr_res, const bool gate_in,
+                          const double rad, const double qq, const double sp, const double qmr_res, const bool gate,
                           const int nsub, const DevPar &P, const semic_bnd &B, const double *tab)
 {
-    // ALLG: every lane of the warp is gated (mask == 2 or snow covered), a compile-time true removes the selects
-    const bool gate = ALLG ? true : gate_in;
-#if !SEMIC_STRICT
-    double ts_raw = ts;                                                        // tsurf of the last sub-step before the clamp
-    const double lat_a = lhf_c * kc[15], lat_b = lhf_c * qq;                   // day constants of latent_q
-    const double radq = rad - qmr_res;                                         // :194 with the day-constant terms first
-#endif
+    (void)tab;
 #pragma unroll UNR
     for (int k = 0; k < nsub; ++k) {
         if (!BND(shf)) shf = shf_c * (ts - t2m);                               // :173
         if (!BND(lhf)) {                                                       // :179-185
-#if SEMIC_STRICT
             const bool ice = ts < c_t0;                                        // :415
             const double q = latent_q(ts, lhf_c, qq, sp, ice);
             lhf = q * (ice ? c_cls : c_clv);                                   // :421,:428
-#else
-            const bool ice = ts < kc[14];
-            const double q = latent_q<ALLG>(ts, lat_a, lat_b, sp, ice, tab);
-            lhf = q * (ice ? kc[22] : kc[23]);
-#endif
             q_last = q;
             ice_last = ice;
             if (GENERIC) { subl = ice ? q : 0.0; evap = ice ? 0.0 : q; }
         }
         if (GENERIC) subl = fdiv(subl, c_rhow);                                // :186 (every sub-step, Q3)
-#if SEMIC_STRICT
         lwu = longwave_upward(ts, c_sigm);                                     // :191
-#else
-        lwu = longwave_upward(ts, kc[17]);
-#endif
-#if SEMIC_STRICT
         const double qsb = (((rad - lwu) - shf) - lhf) - qmr_res;              // :194
         over = 0.0;                                                            // :197
         if (!BND(tsurf)) {                                                     // :198
@@ -414,20 +400,75 @@ DEVI void energy_substeps(double &ts, double &t2m, double &shf, double &lhf, dou
             }
         }
         if (gate) t2m = t2m + fdiv((shf + lhf) * P.tsticsub, P.ceff);          // :209-211 (Q1: forcing t2m is mutated)
-#else
-        const double qsb = ((radq - lwu) - shf) - lhf;
-        if (!BND(tsurf)) {
-            ts_raw = fma(qsb, P.sub_over_ceff, ts);
-            ts = (gate && ts_raw > kc[14]) ? kc[14] : ts_raw;                  // :201-204; the excess is formed after the loop
-        }
-        if (gate) t2m = fma(shf + lhf, P.sub_over_ceff, t2m);
-#endif
     }
-#if !SEMIC_STRICT
-    // only the last sub-step's excess survives (:197, Q2)
-    if (nsub > 0) over = (!BND(tsurf) && gate && ts_raw > kc[14]) ? ts_raw - kc[14] : 0.0;
-#endif
 }
+#else
+// Fast arithmetic.  This translation unit is compiled with -fmad=false: every fused operation below is written as
+// fma(), so all instantiations (unroll factors, compile-time n_ksub, bitmap or not) produce the same bits.
+// ALLG: every lane of the warp is gated (mask == 2 or snow covered) with ts <= t0; a compile-time true removes selects.
+template <bool GENERIC, bool ALLG, int UNR>
+DEVI void energy_substeps(double &ts, double &t2m, double &shf, double &lhf, double &subl, double &evap, double &lwu,
+                          double &q_last, double &over, bool &ice_last, const double shf_c, const double lhf_c,
+                          const double rad, const double qq, const double sp, const double qmr_res, const bool gate_in,
+                          const int nsub, const DevPar &P, const semic_bnd &B, const double *tab)
+{
+    const bool gate = ALLG ? true : gate_in;
+    const double t0 = kc[14], sigm = kc[17], c = P.sub_over_ceff;
+    double ts_raw = ts;                                                        // tsurf of the last sub-step before the clamp
+    const double lat_a = lhf_c * kc[15], lat_b = lhf_c * qq;                   // day constants of latent_q
+    const double radq = rad - qmr_res;                                         // :194 with the day-constant terms first
+    if (!GENERIC) {
+        // the diagnostics shf, lhf, lwu of the last sub-step are formed after the loop from d, q, latent heat and ts^4
+        double d = 0.0, q = 0.0, lat = 0.0, t4 = 0.0;
+        bool ice = false;
+#pragma unroll UNR
+        for (int k = 0; k < nsub; ++k) {
+            ice = ts < t0;                                                     // :415
+            q = latent_q<ALLG>(ts, lat_a, lat_b, sp, ice, tab);                // :179-185
+            lat = ice ? kc[22] : kc[23];
+            d = ts - t2m;                                                      // :173
+            const double t2 = ts * ts;
+            t4 = t2 * t2;                                                      // :191
+            const double lh = lat * q;
+            const double qsb = fma(-shf_c, d, fma(-sigm, t4, radq)) - lh;      // :194
+            ts_raw = fma(qsb, c, ts);                                          // :199
+            if (gate) t2m = fma(fma(shf_c, d, lh), c, t2m);                    // :209-211 (Q1: forcing t2m is mutated)
+            ts = (gate && ts_raw > t0) ? t0 : ts_raw;                          // :201-204; the excess is formed below
+        }
+        if (nsub > 0) {
+            shf = shf_c * d;
+            lhf = lat * q;
+            lwu = sigm * t4;
+            q_last = q;
+            ice_last = ice;
+        }
+    } else {
+#pragma unroll UNR
+        for (int k = 0; k < nsub; ++k) {
+            if (!BND(shf)) shf = shf_c * (ts - t2m);                           // :173
+            if (!BND(lhf)) {                                                   // :179-185
+                const bool ice = ts < t0;
+                const double q = latent_q<false>(ts, lat_a, lat_b, sp, ice, tab);
+                lhf = q * (ice ? kc[22] : kc[23]);
+                q_last = q;
+                ice_last = ice;
+                subl = ice ? q : 0.0;
+                evap = ice ? 0.0 : q;
+            }
+            subl = fdiv(subl, c_rhow);                                         // :186 (every sub-step, Q3)
+            lwu = longwave_upward(ts, sigm);                                   // :191
+            const double qsb = ((radq - lwu) - shf) - lhf;                     // :194
+            if (!BND(tsurf)) {
+                ts_raw = fma(qsb, c, ts);
+                ts = (gate && ts_raw > t0) ? t0 : ts_raw;
+            }
+            if (gate) t2m = fma(shf + lhf, c, t2m);
+        }
+    }
+    // only the last sub-step's excess survives (:197, Q2)
+    if (nsub > 0) over = (!BND(tsurf) && gate && ts_raw > t0) ? ts_raw - t0 : 0.0;
+}
+#endif
 
 
 // `row` points at this point's column of the day's forcing (a shared-memory stage in k_run, global
@@ -455,7 +496,11 @@ DEVI unsigned point_day(Pt &s, const double *row, const long long T, const DevPa
         // exact hoists: literal left-to-right prefixes of :387, :420/:427 and :194
         const double shf_c  = (P.csh_cap * rhoa) * wind;
         const double lhf_c  = (P.clh * wind) * rhoa;
+#if SEMIC_STRICT
         const double rad    = ((1.0 - s.alb) * swd) + row[SEMIC_V_LWD * T];
+#else
+        const double rad    = fma(1.0 - s.alb, swd, row[SEMIC_V_LWD * T]);
+#endif
         const double qq = row[SEMIC_V_QQ * T], sp = row[SEMIC_V_SP * T];
         double q_last = 0.0, over = 0.0;
         bool ice_last = false;
@@ -623,6 +668,7 @@ DEVI unsigned point_day(Pt &s, const double *row, const long long T, const DevPa
             else if (scheme == SCHEME_DENBY)  alb_snow = albedo_denby(melt, P);    // :342-343
             else if (scheme == SCHEME_ISBA)   alb_snow = albedo_isba(alb_snow, sf, melt, P);   // :344-346
             else if (scheme == SCHEME_NONE)   alb_snow = P.alb_smax;               // :347-348
+#if SEMIC_STRICT
             if (mask == 2)      alb = P.albi + (f_alb * (alb_snow - P.albi));      // :350-352
             else if (mask == 1) alb = P.albl + (f_alb * (alb_snow - P.albl));      // :353-355
             else if (mask == 0) alb = 0.06;                                        // :356-358
@@ -630,6 +676,15 @@ DEVI unsigned point_day(Pt &s, const double *row, const long long T, const DevPa
                 alb_snow = P.alb_smin + (P.smax_m_smin * ((0.5 * tanh(P.afac * (t2m - P.tmid))) + 0.5));
                 alb = alb_snow;
             }
+#else
+            if (mask == 2)      alb = fma(f_alb, alb_snow - P.albi, P.albi);
+            else if (mask == 1) alb = fma(f_alb, alb_snow - P.albl, P.albl);
+            else if (mask == 0) alb = 0.06;
+            if (scheme == SCHEME_ALEX) {
+                alb_snow = fma(P.smax_m_smin, fma(0.5, tanh(P.afac * (t2m - P.tmid)), 0.5), P.alb_smin);
+                alb = alb_snow;
+            }
+#endif
         }
         qmr_res = (mask == 0) ? 0.0 : qmr;                                         // :368-372
     }

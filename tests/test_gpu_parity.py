@@ -101,6 +101,84 @@ def test_synthetic_one_year(k, ppt):
     _compare(dict(util.PAR_SLATER, n_ksub=k), (), forc, 365, mask, ppt=ppt, label="synthetic")
 
 
+# ------------------------------------------------------------------------------------------------------------
+# the benchmarked kernel (k_run_lean: 8 output rows, no branch bitmap) against the oracle; the flip taint comes
+# from the bitmap run of the same inputs
+# ------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("scheme,k", [("slater", 3), ("slater", 1), ("slater", 2), ("slater", 5), ("slater", 24),
+                                      ("none", 3), ("isba", 3), ("denby", 3), ("alex", 3), ("unknown", 3)])
+def test_lean_kernel_parity(scheme, k):
+    from semic_b200 import engine
+    g = _gpu()
+    nx, nwin, ndays, out_days = 2048 + 77, 120, 300, 250         # ragged tail, forcing window wraps, spin-up days unwritten
+    fs = engine.Series(nx, 9, nwin).synth_forcing(20260101, point0=31, dayofs=100, daystride=3)
+    forc = fs.download()
+    fs.free()
+    r = np.random.default_rng(7)
+    mask = r.choice(np.array([2, 1, 0], dtype=np.int32), size=nx, p=[0.85, 0.10, 0.05]).astype(np.int32)
+    par = dict(util.SCHEME_PARS[scheme], n_ksub=k)
+    S0, m0 = util.init_slab(nx, mask)
+    fin_l, out_l, _, _ = g.run_gpu(S0, m0, par, (), forc, ndays, out_days=out_days, branch=False)     # k_run_lean
+    # bitmap run over ALL days: a flip during the unwritten spin-up days taints the point as well
+    fin_b, out_b, br_b, _ = g.run_gpu(S0, m0, par, (), forc, ndays, out_days=ndays, branch=True)      # k_run + bitmap
+    fin_o, out_o, br_o = g.run_oracle(S0, m0, par, (), forc, ndays, out_days=ndays)
+    taint = util.tainted(br_b, br_o)[ndays - out_days:]
+    out_b, out_o = out_b[ndays - out_days:], out_o[ndays - out_days:]
+    pts = taint.any(axis=0)
+    oe = util.out_errors(out_l, out_o, exclude=taint)
+    se = util.state_errors(fin_l, fin_o, exclude_points=pts)
+    worst = max(list(oe.values()) + list(se.values()))
+    same = np.array_equal(out_l, out_b) and np.array_equal(fin_l[:23], fin_b[:23])
+    print("\n[lean %s k=%d] max rel err vs oracle %.3e; tainted points %d; bit-identical to the bitmap kernel: %s"
+          % (scheme, k, worst, int(pts.sum()), same))
+    assert worst <= TOL, (oe, se)
+    # the fast translation unit is compiled without implicit FMA contraction and writes its fused operations out, so
+    # every instantiation (compile-time n_ksub, unroll factor, run-time scheme switch, bitmap) rounds alike
+    assert same
+
+
+def test_lean_kernel_output_ring_and_chunks():
+    """daily output into a ring shorter than the run keeps the last days; a run cut into launches continues bit for bit"""
+    from semic_b200 import engine
+    from semic_b200 import surface_physics as spm
+    g = _gpu()
+    nx, nwin, ndays = 1000, 50, 130
+    forc = util.random_forcing(nx, nwin, seed=3)
+    mask = np.full(nx, 2, dtype=np.int32)
+    mask[::9] = 1
+    mask[4::31] = 0
+    S0, m0 = util.init_slab(nx, mask)
+    par_d = dict(util.PAR_SLATER, n_ksub=3)
+    fin_a, out_a, _, _ = g.run_gpu(S0, m0, par_d, (), forc, ndays, out_days=ndays, branch=False)
+    # ring of 16 days, all 130 days written: slot (d % 16) holds the last day that mapped to it
+    par, bnd = g.make_par(par_d), g.make_bnd()
+    st = g.make_state(S0, m0)
+    fs = engine.Series(nx, 9, nwin).upload(forc)
+    ring = engine.Series(nx, 8, 16)
+    engine.run(st, par, bnd, fs, ndays, out=ring, out_days=ndays)
+    o = ring.download()
+    for slot in range(16):
+        d = max(dd for dd in range(ndays) if dd % 16 == slot)
+        assert np.array_equal(o[slot], out_a[d]), slot
+    st.download()
+    assert np.array_equal(st.as_slab()[:23], fin_a[:23])
+    spm.surface_dealloc(st)
+    # three launches (day0 continues the forcing window): same state and same daily fields as one launch
+    st = g.make_state(S0, m0)
+    outs = engine.Series(nx, 8, ndays)
+    d0 = 0
+    got = []
+    for n in (1, 49, 80):
+        engine.run(st, par, bnd, fs, n, day0=d0, out=outs, out_days=n)
+        got.append(outs.download(0, n))
+        d0 += n
+    st.download()
+    assert np.array_equal(st.as_slab()[:23], fin_a[:23])
+    assert np.array_equal(np.concatenate(got, axis=0), out_a)
+    spm.surface_dealloc(st)
+    fs.free(); ring.free(); outs.free()
+
+
 def test_synthetic_statistics():
     """the device generator stays inside the ranges of SURVEY 8(d) / the shipped forcing"""
     from semic_b200 import engine
