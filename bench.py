@@ -206,11 +206,13 @@ def main():
     ap.add_argument("--ppt", type=int, default=0)
     ap.add_argument("--e2e-days", type=int, default=8, help="days per end-to-end (host buffers) step")
     ap.add_argument("--e2e-steps", type=int, default=2)
-    ap.add_argument("--cpu-points-per-core", type=int, default=8192)
+    ap.add_argument("--cpu-points-per-core", type=int, default=65536,
+                    help="CPU sample: points per host core (26 MB of state+forcing per core: not cache resident, like the full grid)")
     ap.add_argument("--cpu-days", type=int, default=365)
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-e2e", action="store_true")
-    ap.add_argument("--extra", action="store_true", help="also time C2 (100k points, n_ksub=24) and C3 at n_ksub=24")
+    ap.add_argument("--extra", action="store_true", help="(default now; kept for compatibility)")
+    ap.add_argument("--no-extra", action="store_true", help="skip the extra figures: C3 at n_ksub=24, C2 (100k points, n_ksub=24)")
     args = ap.parse_args()
 
     if args.impl == "reference":
@@ -308,12 +310,12 @@ def main():
                 hf.array[:, :, c0:c1] = forcing.download(0, wh, c0, c1 - c0)
         ho = engine.PinnedArray((args.e2e_days, 8, N))
         engine.run_host(st, par, bnd, hf.array, min(args.e2e_days, 8), h_out=ho.array[:min(args.e2e_days, 8)],
-                        out_days=min(args.e2e_days, 8), chunk_days=2, ppt=args.ppt)
+                        out_days=min(args.e2e_days, 8), chunk_days=1, ppt=args.ppt)
         barrier()
         tot = 0.0
         for _ in range(args.e2e_steps):
             tot += engine.run_host(st, par, bnd, hf.array, args.e2e_days, h_out=ho.array, out_days=args.e2e_days,
-                                   chunk_days=2, ppt=args.ppt)
+                                   chunk_days=1, ppt=args.ppt)
         barrier()
         if dist is not None:
             import torch
@@ -350,7 +352,7 @@ def main():
         except Exception:
             traffic = None
     roofline = {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
-                "traffic": traffic, "peak_source": peak_src, "kernel": "k_run (persistent multi-day step)",
+                "traffic": traffic, "peak_source": peak_src, "kernel": "k_run_lean (persistent multi-day step)",
                 "algorithmic_bytes_per_point_day": B_FORCING + B_OUT, "launch_ms": launch_ms}
     # second denominator: the path is FP64-pipe / issue bound for larger n_ksub -- measured DFMA peak
     ms = C.c_float(0.0)
@@ -368,13 +370,14 @@ def main():
     if e2e is not None:
         line["e2e"] = e2e
 
-    if args.extra:
+    if not args.no_extra:
         extra = {}
         # C3 at n_ksub=24 on the same buffers
         par24 = make_par(24, args.scheme)
         engine.run(st, par24, bnd, forcing, 30, out=out, out_days=30, ppt=args.ppt)
-        t = engine.run(st, par24, bnd, forcing, args.days, out=out, out_days=args.days, ppt=args.ppt)
+        t = min(engine.run(st, par24, bnd, forcing, args.days, out=out, out_days=args.days, ppt=args.ppt) for _ in range(2))
         extra["C3_n_ksub24_point_days_per_s"] = float(N) * args.days / (t * 1e-3)
+        extra["C3_n_ksub24_note"] = "same buffers, this rank only; FP64-pipe bound (profiles/r01_summary.md), HBM at ~30 %"
         # C2: 100k points, 1 year, n_ksub=24, Greenland-like mask
         st2 = make_state(100000, 0, 0.85, 0.10)
         f2 = engine.Series(100000, 9, 365).synth_forcing(SEED)
