@@ -687,7 +687,7 @@ static int step_on_slab(semic_state *s, const semic_par *par, const semic_bnd *b
 {
     RunArgs a;
     std::memset(&a, 0, sizeof a);
-    a.slab = s->d_slab; a.mask = s->d_mask; a.nx = s->npts; a.ld = s->ld;
+    a.slab = s->d_slab; a.mask = s->d_mask; a.nx = s->npts; a.ld = s->ld; a.sld = s->ld;
     a.forcing = s->d_slab;
     a.f_tiled = 0; a.f_nwin = 1; a.f_day0 = 0;
     const int src_field[kForcingRows] = {SEMIC_F_SF, SEMIC_F_RF, SEMIC_F_SWD, SEMIC_F_LWD, SEMIC_F_WIND, SEMIC_F_SP,
@@ -742,7 +742,7 @@ static void fill_run_args(RunArgs &a, semic_state *now, const semic_par *par, co
                           int out_days)
 {
     std::memset(&a, 0, sizeof a);
-    a.slab = now->d_slab; a.mask = now->d_mask; a.nx = now->npts; a.ld = now->ld;
+    a.slab = now->d_slab; a.mask = now->d_mask; a.nx = now->npts; a.ld = now->ld; a.sld = now->ld;
     a.forcing = forcing;
     a.f_tiled = 1;
     a.f_nwin = f_nwin;
@@ -828,9 +828,11 @@ extern "C" int semic_host_free(void *p)
     return SEMIC_OK;
 }
 
-// Host-streamed run: H2D of chunk c+1 and D2H of chunk c-1 overlap the kernel of chunk c.  Host buffers are SoA
-// per day (the reference's array layout); each chunk is re-tiled on the device (2 x 72 B/point-day of HBM traffic,
-// negligible next to PCIe).
+// Host-streamed run.  The unit of the pipeline is (chunk of days) x (slice of points): H2D of unit u+1 and D2H of unit
+// u-1 overlap the kernel of unit u.  Slicing the points (independent, surface_physics.f90:138-374 has no neighbour
+// terms) keeps the pipeline's fill and drain -- the first H2D and the last D2H, which nothing can overlap -- at a
+// fraction of a day's transfer.  Host buffers are SoA per day (the reference's array layout); each unit is re-tiled
+// on the device (2 x 72 B/point-day of HBM traffic, negligible next to PCIe).
 extern "C" int semic_run_host(semic_state *now, const semic_par *par, const semic_bnd *bnd, const double *h_forcing,
                               const double *h_vali, int nwin, int ldh, int ndays, double *h_out, int out_days,
                               int chunk_days, const semic_run_opts *opts, float *total_ms)
@@ -851,6 +853,12 @@ extern "C" int semic_run_host(semic_state *now, const semic_par *par, const semi
     const bool generic = any_consulted_flag(bnd) || par->n_ksub < 1;
     const int strict = opts ? opts->strict : 0;
     const bool use_vali = h_vali != nullptr && generic;
+    // point slices: multiples of kLdAlign points, about 4 Mi points each (SEMIC_HOST_SLICE overrides, for tests)
+    int slice = 1 << 22;
+    if (const char *e = getenv("SEMIC_HOST_SLICE")) { const int v = atoi(e); if (v > 0) slice = round_up(v, kLdAlign); }
+    if (slice > ld) slice = ld;
+    const int nslices = (npts + slice - 1) / slice;
+    const int sld = slice;                                        // leading dimension of the units' tiled buffers
 
     // per buffer set b: SoA staging (s) and tiled (t) copies of forcing f, vali v, output o
     double *d_fs[2] = {nullptr, nullptr}, *d_ft[2] = {nullptr, nullptr}, *d_vs[2] = {nullptr, nullptr}, *d_vt[2] = {nullptr, nullptr};
@@ -858,8 +866,8 @@ extern "C" int semic_run_host(semic_state *now, const semic_par *par, const semi
     cudaStream_t s_in = nullptr, s_out = nullptr;
     cudaEvent_t ev_in[2] = {nullptr, nullptr}, ev_t[2] = {nullptr, nullptr}, ev_k[2] = {nullptr, nullptr}, ev_o[2] = {nullptr, nullptr};
     cudaEvent_t t0 = nullptr, t1 = nullptr;
-    const size_t fsb = (size_t)chunk_days * SEMIC_NFORCING * npts * 8, ftb = (size_t)chunk_days * SEMIC_NFORCING * ld * 8;
-    const size_t osb = (size_t)chunk_days * SEMIC_NOUT * npts * 8, otb = (size_t)chunk_days * SEMIC_NOUT * ld * 8;
+    const size_t fsb = (size_t)chunk_days * SEMIC_NFORCING * slice * 8, ftb = (size_t)chunk_days * SEMIC_NFORCING * sld * 8;
+    const size_t osb = (size_t)chunk_days * SEMIC_NOUT * slice * 8, otb = (size_t)chunk_days * SEMIC_NOUT * sld * 8;
     int status = SEMIC_OK;
     auto cleanup = [&]() {
         for (int b = 0; b < 2; ++b) {
@@ -896,59 +904,71 @@ extern "C" int semic_run_host(semic_state *now, const semic_par *par, const semi
 
     const int nchunks = (ndays + chunk_days - 1) / chunk_days;
     const int out_first = ndays - out_days;
+    const int dst_field[kForcingRows] = {SEMIC_F_SF, SEMIC_F_RF, SEMIC_F_SWD, SEMIC_F_LWD, SEMIC_F_WIND, SEMIC_F_SP,
+                                         SEMIC_F_RHOA, SEMIC_F_QQ, -1};      // t2m is written by the kernel (mutated)
     CUX(cudaEventRecord(t0, now->stream));
     CUX(cudaStreamWaitEvent(s_in, t0, 0));
+    long long unit = 0;
     for (int c = 0; c < nchunks; ++c) {
-        const int b = c & 1;
         const int d0 = c * chunk_days;
         const int nd = (d0 + chunk_days <= ndays) ? chunk_days : ndays - d0;
-        // H2D of this chunk's SoA rows (day d -> window row d % nwin), once the re-tiling that last read the staging is done
-        if (c >= 2) CUX(cudaStreamWaitEvent(s_in, ev_t[b], 0));
-        int done = 0;
-        while (done < nd) {
-            const int w = (d0 + done) % nwin;
-            const int run = (nd - done < nwin - w) ? nd - done : nwin - w;
-            CUX(cudaMemcpy2DAsync(d_fs[b] + (size_t)done * SEMIC_NFORCING * npts, (size_t)npts * 8,
-                                  h_forcing + (size_t)w * SEMIC_NFORCING * ldh, (size_t)ldh * 8, (size_t)npts * 8,
-                                  (size_t)run * SEMIC_NFORCING, cudaMemcpyHostToDevice, s_in));
-            if (use_vali)
-                CUX(cudaMemcpy2DAsync(d_vs[b] + (size_t)done * SEMIC_NOUT * npts, (size_t)npts * 8,
-                                      h_vali + (size_t)w * SEMIC_NOUT * ldh, (size_t)ldh * 8, (size_t)npts * 8,
-                                      (size_t)run * SEMIC_NOUT, cudaMemcpyHostToDevice, s_in));
-            done += run;
-        }
-        CUX(cudaEventRecord(ev_in[b], s_in));
-        // compute stream: re-tile, run the chunk, de-tile its output days
-        CUX(cudaStreamWaitEvent(now->stream, ev_in[b], 0));
-        k_soa_to_tiled<<<1184, 256, 0, now->stream>>>(d_fs[b], npts, d_ft[b], ld, SEMIC_NFORCING, 0, nd, npts);
-        if (use_vali) k_soa_to_tiled<<<1184, 256, 0, now->stream>>>(d_vs[b], npts, d_vt[b], ld, SEMIC_NOUT, 0, nd, npts);
-        CUX(cudaGetLastError());
-        CUX(cudaEventRecord(ev_t[b], now->stream));
         const int o_lo = out_first > d0 ? out_first : d0;                 // output days of this chunk: [o_lo, d0+nd)
         const int o_n = (d0 + nd > o_lo) ? d0 + nd - o_lo : 0;
-        if (o_n > 0 && c >= 2) CUX(cudaStreamWaitEvent(now->stream, ev_o[b], 0));
-        RunArgs a;
-        fill_run_args(a, now, par, bnd, d_ft[b], nd, use_vali ? d_vt[b] : nullptr, 0, nd, d_ot[b], chunk_days, SEMIC_NOUT, o_n);
-        cudaError_t e = strict ? launch_run_strict(a, generic, now->stream, &launches_total)
-                               : launch_run_fast(a, generic, now->stream, &launches_total);
-        if (e != cudaSuccess) { status = cuda_fail(e, "semic_run_host: kernel launch"); cleanup(); return status; }
-        if (o_n > 0) {
-            k_tiled_to_soa<<<1184, 256, 0, now->stream>>>(d_ot[b], ld, SEMIC_NOUT, 0, o_n, 0, npts, d_os[b], npts);
+        for (int sl = 0; sl < nslices; ++sl, ++unit) {
+            const int b = (int)(unit & 1);
+            const int p0 = sl * slice;
+            const int np = (p0 + slice <= npts) ? slice : npts - p0;
+            // H2D of this unit's SoA rows (day d -> window row d % nwin), once the re-tiling that last read the staging is done
+            if (unit >= 2) CUX(cudaStreamWaitEvent(s_in, ev_t[b], 0));
+            int done = 0;
+            while (done < nd) {
+                const int w = (d0 + done) % nwin;
+                const int run = (nd - done < nwin - w) ? nd - done : nwin - w;
+                CUX(cudaMemcpy2DAsync(d_fs[b] + (size_t)done * SEMIC_NFORCING * np, (size_t)np * 8,
+                                      h_forcing + (size_t)w * SEMIC_NFORCING * ldh + p0, (size_t)ldh * 8, (size_t)np * 8,
+                                      (size_t)run * SEMIC_NFORCING, cudaMemcpyHostToDevice, s_in));
+                if (use_vali)
+                    CUX(cudaMemcpy2DAsync(d_vs[b] + (size_t)done * SEMIC_NOUT * np, (size_t)np * 8,
+                                          h_vali + (size_t)w * SEMIC_NOUT * ldh + p0, (size_t)ldh * 8, (size_t)np * 8,
+                                          (size_t)run * SEMIC_NOUT, cudaMemcpyHostToDevice, s_in));
+                done += run;
+            }
+            CUX(cudaEventRecord(ev_in[b], s_in));
+            // compute stream: re-tile, run the unit, de-tile its output days
+            CUX(cudaStreamWaitEvent(now->stream, ev_in[b], 0));
+            k_soa_to_tiled<<<1184, 256, 0, now->stream>>>(d_fs[b], np, d_ft[b], sld, SEMIC_NFORCING, 0, nd, np);
+            if (use_vali) k_soa_to_tiled<<<1184, 256, 0, now->stream>>>(d_vs[b], np, d_vt[b], sld, SEMIC_NOUT, 0, nd, np);
             CUX(cudaGetLastError());
-        }
-        if (c == nchunks - 1) {
-            int r2 = copy_last_forcing(now, d_ft[b], nd, 0, nd);
-            if (r2) { cleanup(); return r2; }
-        }
-        CUX(cudaEventRecord(ev_k[b], now->stream));
-        if (o_n > 0) {                                                    // D2H of the chunk's output days
-            CUX(cudaStreamWaitEvent(s_out, ev_k[b], 0));
-            CUX(cudaMemcpy2DAsync(h_out + (size_t)(o_lo - out_first) * SEMIC_NOUT * ldh, (size_t)ldh * 8, d_os[b],
-                                  (size_t)npts * 8, (size_t)npts * 8, (size_t)o_n * SEMIC_NOUT, cudaMemcpyDeviceToHost, s_out));
-            CUX(cudaEventRecord(ev_o[b], s_out));
+            CUX(cudaEventRecord(ev_t[b], now->stream));
+            if (o_n > 0 && unit >= 2) CUX(cudaStreamWaitEvent(now->stream, ev_o[b], 0));
+            RunArgs a;
+            fill_run_args(a, now, par, bnd, d_ft[b], nd, use_vali ? d_vt[b] : nullptr, 0, nd, d_ot[b], chunk_days, SEMIC_NOUT, o_n);
+            a.slab = now->d_slab + p0; a.mask = now->d_mask + p0; a.nx = np; a.sld = sld;      // this slice of the points
+            cudaError_t e = strict ? launch_run_strict(a, generic, now->stream, &launches_total)
+                                   : launch_run_fast(a, generic, now->stream, &launches_total);
+            if (e != cudaSuccess) { status = cuda_fail(e, "semic_run_host: kernel launch"); cleanup(); return status; }
+            if (o_n > 0) {
+                k_tiled_to_soa<<<1184, 256, 0, now->stream>>>(d_ot[b], sld, SEMIC_NOUT, 0, o_n, 0, np, d_os[b], np);
+                CUX(cudaGetLastError());
+            }
+            if (c == nchunks - 1) {           // the state's forcing fields hold the last day's forcing, as after the reference's loop
+                for (int v = 0; v < kForcingRows; ++v) {
+                    if (dst_field[v] < 0) continue;
+                    k_tiled_var_to_row<<<(np + 255) / 256, 256, 0, now->stream>>>(d_ft[b], sld, SEMIC_NFORCING, nd - 1, v, np,
+                                                                                now->d_slab + (size_t)dst_field[v] * ld + p0);
+                }
+                CUX(cudaGetLastError());
+            }
+            CUX(cudaEventRecord(ev_k[b], now->stream));
+            if (o_n > 0) {                                                    // D2H of the unit's output days
+                CUX(cudaStreamWaitEvent(s_out, ev_k[b], 0));
+                CUX(cudaMemcpy2DAsync(h_out + (size_t)(o_lo - out_first) * SEMIC_NOUT * ldh + p0, (size_t)ldh * 8, d_os[b],
+                                      (size_t)np * 8, (size_t)np * 8, (size_t)o_n * SEMIC_NOUT, cudaMemcpyDeviceToHost, s_out));
+                CUX(cudaEventRecord(ev_o[b], s_out));
+            }
         }
     }
-    for (int b = 0; b < 2; ++b) if (out_days > 0) CUX(cudaStreamWaitEvent(now->stream, ev_o[b], 0));
+    for (int b = 0; b < 2; ++b) if (out_days > 0 && unit > b) CUX(cudaStreamWaitEvent(now->stream, ev_o[b], 0));
     CUX(cudaEventRecord(t1, now->stream));
     CUX(cudaStreamSynchronize(now->stream));
     CUX(cudaStreamSynchronize(s_out));

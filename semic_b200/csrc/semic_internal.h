@@ -65,6 +65,7 @@ struct RunArgs {
     const int    *mask;
     int           nx;
     int           ld;
+    int           sld;          // leading dimension of the tiled series (forcing, vali, out); = ld except for point slices
     // forcing: tiled series (f_tiled=1, day d -> window row (f_day0+d) % f_nwin), or the slab's own SoA forcing
     // fields (f_tiled=0: variable v of point i at forcing[f_var_off[v] + i]; the drop-in single-day call)
     const double *forcing;

@@ -807,7 +807,7 @@ __global__ void __launch_bounds__(WPC * 32, MINB) k_run(const __grid_constant__ 
     }
 
     const long long ld = a.ld;
-    const long long ntl = ld / kTile;                            // tiles per series row
+    const long long ntl = a.sld / kTile;                         // tiles per series row
     const long long ntiles = ((long long)a.nx + kTile - 1) / kTile;
     const long long nwarps = (long long)gridDim.x * WPC;
     int stage = 0;
@@ -995,7 +995,7 @@ __global__ void __launch_bounds__(WPC * 32, 1) k_run_lean(const __grid_constant_
     __syncthreads();
 
     const long long ld = a.ld;
-    const long long ntl = ld / kTile;
+    const long long ntl = a.sld / kTile;                         // tiles per series row
     const long long ntiles = ((long long)a.nx + kTile - 1) / kTile;
     const long long nwarps = (long long)gridDim.x * WPC;
     const long long f_day = ntl * FBLK;                          // doubles per forcing day

@@ -425,9 +425,14 @@ def test_surface_physics_average():
 # ------------------------------------------------------------------------------------------------------------
 # host-streamed run == device-resident run, bit for bit
 # ------------------------------------------------------------------------------------------------------------
-def test_run_host_equals_run():
+@pytest.mark.parametrize("slice_pts", [0, 1024])
+def test_run_host_equals_run(slice_pts, monkeypatch):
     from semic_b200 import engine
     g = _gpu()
+    if slice_pts:
+        monkeypatch.setenv("SEMIC_HOST_SLICE", str(slice_pts))       # 3 point slices per chunk of days
+    else:
+        monkeypatch.delenv("SEMIC_HOST_SLICE", raising=False)
     nx, nwin, ndays = 3000, 30, 75
     forc = util.random_forcing(nx, nwin, seed=11)
     mask = np.full(nx, 2, dtype=np.int32)
