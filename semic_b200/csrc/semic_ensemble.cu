@@ -84,6 +84,11 @@ extern "C" int semic_ensemble_cost(const semic_state *init, const semic_par *par
     if (f_ld != ld || v_ld != ld) { set_error("semic_ensemble_cost: leading dimensions differ"); status = SEMIC_ERR_ARG; goto done; }
     a.inv_var = d_invvar; a.pars = d_pars; a.npar = npar; a.ntime = ntime; a.nloop = nloop;
     a.partial = d_partial;
+    a.uni_scheme = hp[0].scheme; a.uni_ksub = hp[0].n_ksub;
+    for (int p = 1; p < npar; ++p) {
+        if (hp[p].scheme != a.uni_scheme) a.uni_scheme = -1;
+        if (hp[p].n_ksub != a.uni_ksub) a.uni_ksub = 0;
+    }
     if (npts > 0) {
         CUE(launch_vali_invvar(a, d_invvar, st));
         CUE(cudaEventRecord(e0, st));

@@ -100,6 +100,8 @@ struct EnsArgs {
     int           ntime, nloop;
     double       *partial;      // [npar][ntiles] per-CTA partial sums (deterministic two-stage reduce)
     int           ntiles;       // ceil(nx/32)
+    int           uni_scheme;   // the scheme id all particles share, or -1
+    int           uni_ksub;     // the n_ksub all particles share, or 0
 };
 
 // implemented once per arithmetic mode (semic_kernels_fast.cu / semic_kernels_strict.cu)

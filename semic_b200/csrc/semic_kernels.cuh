@@ -1115,7 +1115,10 @@ __global__ void __launch_bounds__(WPC * 32, 1) k_run_lean(const __grid_constant_
 // 32 points go to partial[particle][tile] (fixed-order second stage: bitwise reproducible).
 constexpr int kEnsParticles = 8;
 
-__global__ void __launch_bounds__(32 * kEnsParticles) k_ensemble(const EnsArgs a, const int ngroups)
+// SCHEME / NK: albedo scheme and n_ksub as compile-time constants when every particle shares them (optimize/tools.py:31,35
+// writes n_ksub = 3 and alb_scheme = "none" into every particle's namelist); SCHEME_RUNTIME / 0 otherwise.
+template <int SCHEME, int NK>
+__global__ void __launch_bounds__(32 * kEnsParticles, 3) k_ensemble(const EnsArgs a, const int ngroups)
 {
     __shared__ DevPar s_par[kEnsParticles];
     __shared__ double tab[kExpTab];
@@ -1160,7 +1163,7 @@ __global__ void __launch_bounds__(32 * kEnsParticles) k_ensemble(const EnsArgs a
         for (int n = 0; n < a.ntime; ++n) {
             const double *row = a.forcing + ((long long)n * ntl + tile) * (kForcingRows * kTile) + lane;
             double swd;
-            point_day<SCHEME_RUNTIME, false, false>(s, row, kTile, P, B, P.n_ksub, 1, swd, tab);
+            point_day<SCHEME, false, false, (NK > 0 ? NK : 2), NK>(s, row, kTile, P, B, P.n_ksub, 1, swd, tab);
             if (lastloop) {                                              // run_particles.f90:148-157
                 const double *v = a.vali + ((long long)n * ntl + tile) * (SEMIC_NOUT * kTile) + lane;
                 double d[4];

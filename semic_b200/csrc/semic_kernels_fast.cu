@@ -93,7 +93,15 @@ cudaError_t launch_ensemble_fast(const EnsArgs &a, double *sumsq_dev, cudaStream
     const int ngroups = (a.npar + fast_mode::kEnsParticles - 1) / fast_mode::kEnsParticles;
     const long long nblocks = (long long)a.ntiles * ngroups;
     if (nblocks > 0x7fffffffLL) return cudaErrorInvalidValue;
-    fast_mode::k_ensemble<<<(unsigned)nblocks, 32 * fast_mode::kEnsParticles, 0, st>>>(a, ngroups);
+    const dim3 grid((unsigned)nblocks), block(32 * fast_mode::kEnsParticles);
+    const bool k3 = a.uni_ksub == 3;
+    if (a.uni_scheme == SCHEME_NONE) {
+        if (k3) fast_mode::k_ensemble<SCHEME_NONE, 3><<<grid, block, 0, st>>>(a, ngroups);
+        else    fast_mode::k_ensemble<SCHEME_NONE, 0><<<grid, block, 0, st>>>(a, ngroups);
+    } else {
+        if (k3) fast_mode::k_ensemble<SCHEME_RUNTIME, 3><<<grid, block, 0, st>>>(a, ngroups);
+        else    fast_mode::k_ensemble<SCHEME_RUNTIME, 0><<<grid, block, 0, st>>>(a, ngroups);
+    }
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return e;
     fast_mode::k_ens_reduce<<<(a.npar + 127) / 128, 128, 0, st>>>(a.partial, a.ntiles, a.npar, sumsq_dev);
