@@ -390,6 +390,24 @@ def main():
         par3 = make_par(3, args.scheme)
         ts = [engine.run(st2, par3, bnd, f2, 365, out=o2, out_days=365) for _ in range(5)]
         extra["C2_100k_points_n_ksub3_point_days_per_s"] = 100000.0 * 365 / (min(ts) * 1e-3)
+        # C5: parameter ensemble, 1024 parameter sets x 100k points x 365 days, n_ksub=3, alb_scheme "none" (tools.py:31,35);
+        # validation series = the model's own daily output with the default parameters (device resident, no host leg)
+        try:
+            from semic_b200 import driver
+            rng = np.random.default_rng(SEED)
+            names = ["hcrit", "alb_smax", "amp", "rcrit", "albi", "albl"]                 # optimize/namelist.ranges
+            lo_r = np.array([0.0, 0.80, 0.0, 0.0, 0.35, 0.05]); hi_r = np.array([0.5, 0.9, 5.0, 1.0, 0.55, 0.40])
+            P = 1024
+            u = (np.stack([rng.permutation(P) for _ in range(6)], axis=1) + rng.uniform(size=(P, 6))) / P
+            pars = driver.particle_params(names, [{"id": i, "pos": list(lo_r + (hi_r - lo_r) * u[i])} for i in range(P)])
+            st5 = make_state(100000, 0, 0.85, 0.10)
+            engine.run(st2, par3, bnd, f2, 365, out=o2, out_days=365)                     # o2: "observations"
+            engine.ensemble_cost(st5, pars[:8], bnd, f2, o2, 365, 1)
+            ms5 = min(engine.ensemble_cost(st5, pars, bnd, f2, o2, 365, 1)[1] for _ in range(2))
+            extra["C5_ensemble_1024x100k_trajectory_days_per_s"] = 1024 * 100000.0 * 365 / (ms5 * 1e-3)
+            extra["C5_ms"] = ms5
+        except Exception as e:                                                            # never lose the headline line
+            extra["C5_error"] = str(e)[:200]
         line["extra"] = extra
 
     if not args.no_cpu:
