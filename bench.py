@@ -172,7 +172,7 @@ def run_reference_arm(args):
             "cpu_baseline": {"value": value, "unit": "point-days/s", "cores": cores, "kind": "port", "sample": sample},
             "e2e": {"value": value, "unit": "point-days/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
-    print(json.dumps(line))
+    _emit(json.dumps(line))
     return 0
 
 
@@ -416,11 +416,19 @@ def main():
                                 "sample": "%d cores x %d points x %d days, best of 2 (array-form C oracle of surface_physics.f90, "
                                           "gcc -O3 -fno-fast-math -ffp-contract=off; no Fortran compiler in the image)"
                                           % (cores, args.cpu_points_per_core, args.cpu_days), "seconds": sec}
-    print(json.dumps(line))
+    _emit(json.dumps(line))
     if dist is not None:
         dist.destroy_process_group()
     return 0
 
 
+def _emit(line_text):
+    os.write(_REAL_STDOUT, (line_text + "\n").encode())
+
+
 if __name__ == "__main__":
+    # stdout carries exactly ONE line, the JSON: libraries that log to fd 1 (NCCL prints its version there) go to stderr
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
     sys.exit(main())
