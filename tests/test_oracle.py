@@ -67,6 +67,34 @@ def test_tripwire_vectors_from_survey():
                                              0.922055427668082, 1.070329879337655, 1.156530516182002], rtol=0, atol=1e-11)
 
 
+def test_example_run_stays_in_the_band_of_the_shipped_validation_data():
+    """The reference ships no SEMIC output, but it ships what its own workflow validates against: MAR fields next to
+    every forcing file (example/Readme.md:51-61), compared by example/plot_example.py:57-60 through the Pearson
+    correlation and the centred RMSE.  The oracle's `make run_example` twin (example.namelist, 100 loops) must land
+    where the tuned model lands: a weak anchor, but one a wrong restatement of the energy balance does not survive."""
+    forc, vali = util.load_fixture("transect")
+    mask = np.array([1, 1, 1, 2, 2, 2, 2], dtype=np.int32)                    # example.namelist:5
+    S, m = util.init_slab(7, mask, hsnow=5.0, alb=np.float64(np.float32(0.8)))
+    out, _ = ob.run(S, m, ob.make_par(util.PAR_EXAMPLE), ob.make_bnd(), forc, 100 * 365, out_days=365)
+
+    def stats(v, p):
+        x1, x2 = out[:, v, p], vali[:, v, p]
+        r = np.corrcoef(x1, x2)[0, 1]
+        crmse = np.sqrt(np.sum(((x1 - x1.mean()) - (x2 - x2.mean())) ** 2) / len(x1))      # plot_example.py:60
+        return r, crmse, (x1 - x2).mean()
+
+    for p in range(7):
+        r, crmse, bias = stats(0, p)                                           # surface temperature [K]
+        assert r > 0.96 and crmse < 4.0 and abs(bias) < 0.6, (p, r, crmse, bias)
+        r, crmse, bias = stats(2, p)                                           # net shortwave [W/m2]
+        assert r > 0.85 and crmse < 50.0 and abs(bias) < 20.0, (p, r, crmse, bias)
+    for p in range(3, 7):                                                      # ice points: melt season is captured
+        r, crmse, bias = stats(4, p)
+        assert r > 0.7, (p, r)
+        r, crmse, bias = stats(7, p)                                           # latent heat flux [W/m2]
+        assert r > 0.7 and crmse < 6.0, (p, r, crmse)
+
+
 @pytest.mark.parametrize("scheme", ["none", "slater", "isba", "denby", "alex", "unknown"])
 @pytest.mark.parametrize("bnd_names", [(), ("tsurf", "alb"), ("melt", "refr", "amp"), ("shf", "lhf", "acc", "smb")])
 def test_oracle_equals_independent_python_restatement(scheme, bnd_names):
