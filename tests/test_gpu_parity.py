@@ -575,3 +575,52 @@ def test_run_example_program(tmp_path):
     # the state object holds the last day, like the reference's `surface%now` after the loop
     assert np.allclose(np.array(now.tsurf)[ice], ref[-1, 0, ice], rtol=1e-12)
     assert np.array_equal(np.array(now.sf), forc[364, 0, :]) and np.array_equal(np.array(now.qq), forc[364, 7, :])
+
+
+# ------------------------------------------------------------------------------------------------------------
+# the native command-line drivers: example.x == the Python driver == the oracle; run_particles.x == driver.run_particles
+# ------------------------------------------------------------------------------------------------------------
+def test_example_x_native_program(tmp_path):
+    import os
+    import subprocess
+    from semic_b200 import driver
+    from tests.test_host_api import ROOT, _example_dir
+    d = _example_dir(tmp_path, nloop=3)
+    r = subprocess.run([os.path.join(ROOT, "semic_b200", "bin", "example.x"), "example.namelist"], cwd=str(d),
+                       capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    assert "end example program" in r.stdout
+    native = np.loadtxt(d / "example.out")                               # plot_example.py reads it the same way
+    assert native.shape == (365, 56)
+    out, now, par, bnd = driver.run_example(str(d / "example.namelist"), write_output=False)
+    assert np.array_equal(native.reshape(365, 8, 7), out)                # same library, same launch: bit for bit
+
+
+def test_run_particles_x_native_program(tmp_path):
+    import os
+    import subprocess
+    from semic_b200 import driver
+    from tests.test_host_api import ROOT, _example_dir
+    d = _example_dir(tmp_path, nloop=2)
+    forc, vali = util.load_fixture("transect")
+    (d / "optimization.namelist").write_text((d / "example.namelist").read_text())
+    names = ["hcrit", "alb_smax", "amp", "rcrit", "albi", "albl"]                                # optimize/namelist.ranges
+    r = np.random.default_rng(4)
+    lo = np.array([0.01, 0.80, 0.5, 0.0, 0.35, 0.05])
+    hi = np.array([0.5, 0.9, 5.0, 1.0, 0.55, 0.40])
+    pop = [{"id": i, "pos": list(lo + (hi - lo) * r.uniform(size=6))} for i in range(5)]
+    for p in pop:                                                        # what optimize/tools.py:7-43 writes
+        lines = ["&surface_physics", '  boundary = "", "", "",', "  tstic = 86400.0,", "  ceff = 2.0e6,", "  csh = 2.0e-3,",
+                 "  clh = 5.0e-4,", "  tmin = 263.15,", "  tmax = 273.15,", "  afac = -0.18,", "  tmid = 275.35,",
+                 "  n_ksub = 3,", '  alb_scheme = "none",']
+        lines += ["  %s = %.8f," % (n, v) for n, v in zip(names, p["pos"])]
+        (d / ("p_%06d.nml" % p["id"])).write_text("\n".join(lines + ["/", ""]))
+    res = subprocess.run([os.path.join(ROOT, "semic_b200", "bin", "run_particles.x"), '"p_"', "0", "9"], cwd=str(d),
+                         capture_output=True, text=True)
+    assert res.returncode == 0, res.stderr
+    assert "p_000005.nml' not found, exiting loop" in res.stdout
+    native = np.array([float(open(d / ("p_%06d.out" % i)).read()) for i in range(5)])
+    mask = np.array([1, 1, 1, 2, 2, 2, 2], dtype=np.int32)
+    init = dict(hsnow=1.0, hice=0.0, alb=vali[0, 1, :], tsurf=vali[0, 0, :], alb_snow=vali[0, 1, :])     # run_particles.f90:77-82
+    cost = driver.run_particles(pop, names, forc, vali, mask, init, 365, 2)
+    assert np.allclose(native, [cost[i] for i in range(5)], rtol=1e-12, atol=0)

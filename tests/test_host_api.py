@@ -22,6 +22,13 @@ def _declared_symbols():
     return sorted(set(re.findall(r"\b(semic_[a-z0-9_]+)\s*\(", hdr)))
 
 
+def _have_gpu():
+    try:
+        return _capi.lib().semic_device_count() > 0
+    except Exception:
+        return False
+
+
 def test_library_exports_every_declared_symbol():
     names = _declared_symbols()
     assert len(names) >= 50
@@ -199,3 +206,45 @@ def test_numpy_forcing_generator_ranges():
     m = synth.mask(200000)
     frac = np.bincount(m, minlength=3) / m.size
     assert abs(frac[2] - 0.85) < 0.01 and abs(frac[1] - 0.10) < 0.01
+
+
+# ------------------------------------------------------------------------------------------------------------
+# the native command-line drivers (semic_b200/csrc/drivers): host logic runs anywhere, compute fails loudly without a GPU
+# ------------------------------------------------------------------------------------------------------------
+def _example_dir(tmp_path, nloop=2):
+    from tests import util
+    forc, vali = util.load_fixture("transect")
+    (tmp_path / "data").mkdir()
+    np.savetxt(tmp_path / "data" / "transect_input.txt", forc.reshape(365, -1))
+    np.savetxt(tmp_path / "data" / "transect_output.txt", vali.reshape(365, -1))
+    nml = open(util.GOLDEN + "/example.nml").read().replace("nloop = 100", "nloop = %d" % nloop)
+    (tmp_path / "example.namelist").write_text(nml)
+    return tmp_path
+
+
+def test_example_x_host_side_and_loud_failure_without_gpu(tmp_path):
+    import subprocess
+    exe = os.path.join(ROOT, "semic_b200", "bin", "example.x")
+    assert os.path.exists(exe), "run `make -C semic_b200/csrc` (or __graft_entry__.build())"
+    d = _example_dir(tmp_path)
+    r = subprocess.run([exe, "example.namelist"], cwd=str(d), capture_output=True, text=True)
+    # namelist, both ASCII tables and print_param are host side (example.f90:52-68)
+    assert "Read forcing from file" in r.stdout and "Read validation from file" in r.stdout
+    assert "alb_smax" in r.stdout and "0.810000" in r.stdout
+    if not _have_gpu():
+        assert r.returncode != 0 and "CUDA" in r.stderr and not (d / "example.out").exists()
+    r = subprocess.run([exe], cwd=str(d), capture_output=True, text=True)                        # example.f90:38-42
+    assert r.returncode != 0 and "Namelist file is missing" in r.stderr
+    r = subprocess.run([exe, "nope.namelist"], cwd=str(d), capture_output=True, text=True)       # example.f90:44-48
+    assert r.returncode != 0 and "not found" in r.stderr
+
+
+def test_run_particles_x_stops_at_the_first_missing_namelist(tmp_path):
+    import subprocess
+    exe = os.path.join(ROOT, "semic_b200", "bin", "run_particles.x")
+    assert os.path.exists(exe)
+    d = _example_dir(tmp_path)
+    (d / "optimization.namelist").write_text((d / "example.namelist").read_text())
+    r = subprocess.run([exe, '"p_"', "0", "3"], cwd=str(d), capture_output=True, text=True)      # no p_000000.nml: nothing to do
+    assert r.returncode == 0 and "p_000000.nml' not found, exiting loop" in r.stdout              # run_particles.f90:110-113
+    assert "end particle calculation" in r.stdout
