@@ -130,7 +130,7 @@ DEVI double fexp(double x)
     return __hiloint2double(__double2hiint(p) + (k << 20), __double2loint(p));
 }
 // Table-driven exp for the hot loop: exp(x) = 2^k * 2^(j/2048) * p(r), n = rint(x*2048/ln2) = 2048k + j,
-// |r| <= ln2/4096, p = degree-3 Taylor (truncation r^4/24 <= 3.4e-17).  9 FP64 operations; the table lives in shared
+// |r| <= ln2/4096, p = degree-3 Taylor (truncation r^4/24 <= 3.4e-17).  8 FP64 operations; the table lives in shared
 // memory (LDS with a lane-varying index).  |x| < 700, no specials.
 DEVI double fexp_t(double x, const double *tab)
 {
@@ -140,9 +140,10 @@ DEVI double fexp_t(double x, const double *tab)
     double r = fma(nf, kt[2], x);
     r = fma(nf, kt[3], r);
     const double r2 = r * r;
-    const double p01 = r + 1.0;
     const double p23 = fma(kt[5], r, kt[4]);
-    const double p = fma(p23, r2, p01) * tab[n & (kExpTab - 1)];
+    const double em1 = fma(p23, r2, r);                           // e^r - 1
+    const double tj = tab[n & (kExpTab - 1)];
+    const double p = fma(em1, tj, tj);
     return __hiloint2double(__double2hiint(p) + ((n >> 11) << 20), __double2loint(p));
 }
 // asin(s) = s + s*z*R(z), z = s*s <= 1/4: degree-11 interpolant of R at the Chebyshev nodes of [0, 1/4]
