@@ -378,6 +378,16 @@ def main():
         t = min(engine.run(st, par24, bnd, forcing, args.days, out=out, out_days=args.days, ppt=args.ppt) for _ in range(2))
         extra["C3_n_ksub24_point_days_per_s"] = float(N) * args.days / (t * 1e-3)
         extra["C3_n_ksub24_note"] = "same buffers, this rank only; FP64-pipe bound (profiles/r01_summary.md), HBM at ~30 %"
+        # C3 with 30-day means instead of daily rows (in-kernel surface_physics_average): 72 + 64/30 B/point-day
+        try:
+            means = engine.Series(N, 8, 13)
+            engine.run(st, par, bnd, forcing, 60, out=means, out_days=60, avg_days=30)
+            t = min(engine.run(st, par, bnd, forcing, args.days, out=means, out_days=args.days, avg_days=30) for _ in range(3))
+            extra["C3_monthly_means_point_days_per_s"] = float(N) * args.days / (t * 1e-3)
+            extra["C3_monthly_means_note"] = "n_ksub=%d, rows of the output = 30-day means (13 rows per year); issue/FP64 bound" % args.n_ksub
+            means.free()
+        except Exception as e:
+            extra["C3_monthly_means_error"] = str(e)[:200]
         # C2: 100k points, 1 year, n_ksub=24, Greenland-like mask
         st2 = make_state(100000, 0, 0.85, 0.10)
         f2 = engine.Series(100000, 9, 365).synth_forcing(SEED)

@@ -151,7 +151,11 @@ typedef struct semic_run_opts {
     int strict;        /* 0 = fast math (default), 1 = reference operation order, IEEE div, no FMA contraction */
     int out_days;      /* write daily output for the LAST out_days days of the run (0 = none)       */
     int ppt;           /* reserved (points per thread; one point per thread measured fastest)         */
-    int reserved[5];
+    int avg_days;      /* > 1: the rows of `out` are the MEANS of the 8 daily fields over consecutive periods
+                          of avg_days days of the last out_days days (last period may be shorter) -- the protocol of
+                          surface_physics_average (surface_physics.f90:565-629: init / step / end) kept in registers.
+                          Plain runs only (no boundary overrides, 8-row output, fast arithmetic). 0 or 1 = daily rows */
+    int reserved[4];
 } semic_run_opts;
 
 /* Runs ndays days: day d uses forcing row (day0 + d) % ndays(forcing).  `vali` (8 vars, same window)

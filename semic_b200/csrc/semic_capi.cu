@@ -804,6 +804,14 @@ extern "C" int semic_run(semic_state *now, const semic_par *par, const semic_bnd
                   out ? out->ndays : 1, out ? out->nvar : SEMIC_NOUT, out_days);
     const bool generic = any_consulted_flag(bnd) || par->n_ksub < 1;
     const int strict = opts ? opts->strict : 0;
+    a.avg_days = (opts && out_days > 0 && opts->avg_days > 1) ? opts->avg_days : 0;
+    if (a.avg_days > 1) {
+        if (generic || strict || out->nvar != SEMIC_NOUT) {
+            set_error("semic_run: avg_days needs a plain run (no boundary overrides, fast arithmetic, 8-row output)");
+            return SEMIC_ERR_ARG;
+        }
+        if (out->ndays < 1) { set_error("semic_run: empty output series"); return SEMIC_ERR_ARG; }
+    }
     CU(cudaEventRecord(now->ev0, now->stream));
     cudaError_t e = strict ? launch_run_strict(a, generic, now->stream, &launches_total)
                            : launch_run_fast(a, generic, now->stream, &launches_total);

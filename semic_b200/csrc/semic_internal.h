@@ -80,6 +80,7 @@ struct RunArgs {
     int           o_nring;
     int           o_nvar;       // 8, or 9 with the branch bitmap
     int           out_start;    // first day (0-based within this run) that is written
+    int           avg_days;     // > 1: rows of `out` are means over periods of avg_days days (k_run_lean only)
     int           ndays;
     int           eb_steps;     // sub-steps of energy_balance per day (n_ksub; 1 for energy_balance alone; 0 = skip)
     int           do_mb;        // run mass_balance

@@ -971,7 +971,10 @@ DEVI bool elect_one()
     return pred != 0;
 }
 
-template <int SCHEME, int WPC, int UNR, int NK>
+// AVG: instead of every day's 8 fields, their means over consecutive periods of a.avg_days days are written (the
+// surface_physics_average protocol, surface_physics.f90:565-629: zero at 'init', add at every 'step', divide by the
+// number of steps at 'end'), accumulated in registers: the daily 64 B/point of output traffic become 64/avg_days.
+template <int SCHEME, int WPC, int UNR, int NK, bool AVG = false>
 __global__ void __launch_bounds__(WPC * 32, 1) k_run_lean(const __grid_constant__ RunArgs a)
 {
     using SM = RunSmem<false, WPC>;
@@ -1045,6 +1048,9 @@ __global__ void __launch_bounds__(WPC * 32, 1) k_run_lean(const __grid_constant_
         }
         double *oday = a.out + tile * OBLK + lane;
         int oslot = 0;
+        double avg[SEMIC_NOUT] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
+        int navg = 0;
+        (void)avg; (void)navg;
 
         for (int d = 0; d < ndays; ++d) {
             mbar_wait(bar_u + 8u * stage, phase);
@@ -1052,16 +1058,36 @@ __global__ void __launch_bounds__(WPC * 32, 1) k_run_lean(const __grid_constant_
             double swd;
             point_day<SCHEME, false, false, UNR, NK>(s, row, kTile, a.P, a.B, 0, 1, swd, tab);
             if (d >= ostart) {                                   // example.f90:117-122
-                oday[SEMIC_O_STT * kTile]   = s.tsurf;
-                oday[SEMIC_O_ALB * kTile]   = s.alb;
-                oday[SEMIC_O_SWNET * kTile] = swd * (1.0 - s.alb);
-                oday[SEMIC_O_SMB * kTile]   = s.smb;
-                oday[SEMIC_O_MELT * kTile]  = s.melt;
-                oday[SEMIC_O_ACC * kTile]   = s.acc;
-                oday[SEMIC_O_SHF * kTile]   = s.shf;
-                oday[SEMIC_O_LHF * kTile]   = s.lhf;
-                oday += o_day;
-                if (++oslot == a.o_nring) { oslot = 0; oday -= (long long)a.o_nring * o_day; }
+                if (!AVG) {
+                    oday[SEMIC_O_STT * kTile]   = s.tsurf;
+                    oday[SEMIC_O_ALB * kTile]   = s.alb;
+                    oday[SEMIC_O_SWNET * kTile] = swd * (1.0 - s.alb);
+                    oday[SEMIC_O_SMB * kTile]   = s.smb;
+                    oday[SEMIC_O_MELT * kTile]  = s.melt;
+                    oday[SEMIC_O_ACC * kTile]   = s.acc;
+                    oday[SEMIC_O_SHF * kTile]   = s.shf;
+                    oday[SEMIC_O_LHF * kTile]   = s.lhf;
+                } else {
+                    avg[SEMIC_O_STT]   += s.tsurf;               // field_average 'step' (:614)
+                    avg[SEMIC_O_ALB]   += s.alb;
+                    avg[SEMIC_O_SWNET] += swd * (1.0 - s.alb);
+                    avg[SEMIC_O_SMB]   += s.smb;
+                    avg[SEMIC_O_MELT]  += s.melt;
+                    avg[SEMIC_O_ACC]   += s.acc;
+                    avg[SEMIC_O_SHF]   += s.shf;
+                    avg[SEMIC_O_LHF]   += s.lhf;
+                    ++navg;
+                }
+                if (!AVG || navg == a.avg_days || d == ndays - 1) {
+                    if (AVG) {
+                        const double nt = (double)navg;          // 'end' (:621): IEEE division by the number of steps
+#pragma unroll
+                        for (int q = 0; q < SEMIC_NOUT; ++q) { oday[q * kTile] = avg[q] / nt; avg[q] = 0.0; }   // 'init' (:611)
+                        navg = 0;
+                    }
+                    oday += o_day;
+                    if (++oslot == a.o_nring) { oslot = 0; oday -= (long long)a.o_nring * o_day; }
+                }
             }
             if (d == dlast) {                   // final state: all 23 non-forcing fields, as after the reference's last call
                 double *S = a.slab + i;

@@ -65,12 +65,11 @@ cudaError_t launch_run_fast(const RunArgs &a, bool generic, cudaStream_t st, int
     const char *e = getenv("SEMIC_SHAPE");
     const int shape = e ? atoi(e) * 10 + (strchr(e, 'x') ? atoi(strchr(e, 'x') + 1) : 0) : 240;
     const bool lean_ok = a.f_tiled && a.ndays >= 1 && a.P.n_ksub >= 1 && (a.out == nullptr || a.o_nvar == SEMIC_NOUT);
-    if (lean_ok && (shape == 240 || shape == 200)) {                         // "24x0" / "20x0": k_run_lean
-        return shape == 200 ? fast_mode::launch_lean<20>(a, st) : fast_mode::launch_lean<24>(a, st);
-    }
+    if (a.out != nullptr && a.avg_days > 1 && !lean_ok) return cudaErrorNotSupported;   // period means: plain runs only
+    if (lean_ok && (shape == 240 || (a.out != nullptr && a.avg_days > 1))) return fast_mode::launch_lean(a, st);   // "24x0": k_run_lean
     switch (shape) {
         case 82:  return fast_mode::launch_scheme<false, 2, 8>(a, st);       // 16 warps, <=128 regs
-        case 240: case 200: case 242: case 241:                                   // one CTA of 24 warps
+        case 240: case 242: case 241:                                   // one CTA of 24 warps
             return a.P.n_ksub >= 8 ? fast_mode::launch_scheme<false, 1, 24, 4>(a, st) : fast_mode::launch_scheme<false, 1, 24, 2>(a, st);
         case 201: return fast_mode::launch_scheme<false, 1, 20>(a, st);      // one CTA of 20 warps, <=96 regs
         case 162: return fast_mode::launch_scheme<false, 2, 16>(a, st);      // 32 warps, <=64 regs

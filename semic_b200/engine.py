@@ -55,12 +55,14 @@ class Series(object):
             pass
 
 
-def run(state, par, bnd, forcing, ndays, vali=None, day0=0, out=None, out_days=0, strict=False, ppt=0):
-    """semic_run: ndays days of the persistent kernel on device-resident forcing.  Returns kernel ms."""
+def run(state, par, bnd, forcing, ndays, vali=None, day0=0, out=None, out_days=0, strict=False, ppt=0, avg_days=0):
+    """semic_run: ndays days of the persistent kernel on device-resident forcing.  Returns kernel ms.
+    avg_days > 1: rows of `out` are means over consecutive periods of avg_days days (in-kernel surface_physics_average)."""
     opts = SemicRunOpts()
     opts.strict = 1 if strict else 0
     opts.out_days = int(out_days)
     opts.ppt = int(ppt)
+    opts.avg_days = int(avg_days)
     ms = C.c_float(0.0)
     check(lib().semic_run(state.handle, C.byref(par._c), C.byref(bnd._c), forcing.handle,
                           vali.handle if vali is not None else None, int(day0), int(ndays),

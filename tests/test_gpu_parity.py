@@ -179,6 +179,44 @@ def test_lean_kernel_output_ring_and_chunks():
     fs.free(); ring.free(); outs.free()
 
 
+def test_period_means_in_kernel():
+    """opts.avg_days: the rows of `out` are the means of the 8 daily fields over consecutive periods, accumulated
+    in registers with the protocol of surface_physics_average (surface_physics.f90:565-629): bit-identical to
+    adding the daily rows in order and dividing by the number of days."""
+    from semic_b200 import engine
+    from semic_b200 import surface_physics as spm
+    g = _gpu()
+    nx, nwin, ndays, out_days, period = 1500, 60, 200, 170, 30         # 5 full periods + one of 20 days
+    forc = util.random_forcing(nx, nwin, seed=8)
+    mask = np.full(nx, 2, dtype=np.int32)
+    mask[::6] = 1
+    mask[3::40] = 0
+    S0, m0 = util.init_slab(nx, mask)
+    for k in (3, 4):                                                     # compile-time and run-time n_ksub instantiations
+        par_d = dict(util.PAR_SLATER, n_ksub=k)
+        fin_a, out_a, _, _ = g.run_gpu(S0, m0, par_d, (), forc, ndays, out_days=out_days, branch=False)
+        par, bnd = g.make_par(par_d), g.make_bnd()
+        st = g.make_state(S0, m0)
+        fs = engine.Series(nx, 9, nwin).upload(forc)
+        nper = (out_days + period - 1) // period
+        means = engine.Series(nx, 8, nper)
+        engine.run(st, par, bnd, fs, ndays, out=means, out_days=out_days, avg_days=period)
+        got = means.download()
+        st.download()
+        assert np.array_equal(st.as_slab()[:23], fin_a[:23])              # the state does not depend on the output mode
+        for p in range(nper):
+            days = out_a[p * period:(p + 1) * period]
+            acc = np.zeros_like(days[0])
+            for d in range(days.shape[0]):
+                acc = acc + days[d]                                       # field_average 'step' (:614), in day order
+            assert np.array_equal(got[p], acc / float(days.shape[0])), (k, p)     # 'end' (:621)
+        # overrides / bitmap / strict runs keep daily rows only
+        with pytest.raises(Exception):
+            engine.run(st, par, g.make_bnd(("tsurf",)), fs, ndays, out=means, out_days=out_days, avg_days=period)
+        spm.surface_dealloc(st)
+        fs.free(); means.free()
+
+
 def test_synthetic_statistics():
     """the device generator stays inside the ranges of SURVEY 8(d) / the shipped forcing"""
     from semic_b200 import engine
