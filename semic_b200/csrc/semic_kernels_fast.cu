@@ -61,21 +61,15 @@ cudaError_t launch_run_fast(const RunArgs &a, bool generic, cudaStream_t st, int
     if (launches) ++*launches;
     if (cudaError_t e = ensure_exp_table()) return e;
     if (generic) return fast_mode::launch_scheme<true, 1, 8>(a, st);
-    // tuning knob SEMIC_SHAPE = "<warps per CTA>x<CTAs per SM>" (default 8x3: 24 warps per SM at <= 80 registers)
+    // Plain runs go to k_run_lean; what it does not cover (the bitmap row, the drop-in single day on the slab's own
+    // forcing fields, n_ksub < 1) runs k_run.  SEMIC_SHAPE=24x1 forces k_run for A/B timing (tools/ab.py).
     const char *e = getenv("SEMIC_SHAPE");
-    const int shape = e ? atoi(e) * 10 + (strchr(e, 'x') ? atoi(strchr(e, 'x') + 1) : 0) : 240;
+    const bool force_general = e && std::strcmp(e, "24x1") == 0;
     const bool lean_ok = a.f_tiled && a.ndays >= 1 && a.P.n_ksub >= 1 && (a.out == nullptr || a.o_nvar == SEMIC_NOUT);
-    if (a.out != nullptr && a.avg_days > 1 && !lean_ok) return cudaErrorNotSupported;   // period means: plain runs only
-    if (lean_ok && (shape == 240 || (a.out != nullptr && a.avg_days > 1))) return fast_mode::launch_lean(a, st);   // "24x0": k_run_lean
-    switch (shape) {
-        case 82:  return fast_mode::launch_scheme<false, 2, 8>(a, st);       // 16 warps, <=128 regs
-        case 240: case 242: case 241:                                   // one CTA of 24 warps
-            return a.P.n_ksub >= 8 ? fast_mode::launch_scheme<false, 1, 24, 4>(a, st) : fast_mode::launch_scheme<false, 1, 24, 2>(a, st);
-        case 201: return fast_mode::launch_scheme<false, 1, 20>(a, st);      // one CTA of 20 warps, <=96 regs
-        case 162: return fast_mode::launch_scheme<false, 2, 16>(a, st);      // 32 warps, <=64 regs
-        case 84:  return fast_mode::launch_scheme<false, 4, 8>(a, st);       // 32 warps, <=64 regs
-        default:  return fast_mode::launch_scheme<false, 3, 8>(a, st);
-    }
+    const bool want_avg = a.out != nullptr && a.avg_days > 1;
+    if (want_avg && !lean_ok) return cudaErrorNotSupported;                  // period means: plain runs only
+    if (lean_ok && (want_avg || !force_general)) return fast_mode::launch_lean(a, st);
+    return a.P.n_ksub >= 8 ? fast_mode::launch_scheme<false, 1, 24, 4>(a, st) : fast_mode::launch_scheme<false, 1, 24, 2>(a, st);
 }
 
 cudaError_t launch_vali_invvar(const EnsArgs &a, double *inv_var, cudaStream_t st)

@@ -1,5 +1,6 @@
 """Sustained A/B timing of k_run variants on the bench workload (16.7 M points x 365 days, M1 output into a 32-day ring).
-   Variants (SEMIC_SHAPE values, read by the library at every launch) are run in alternating blocks of `steps`
+   Variants (SEMIC_SHAPE values, read by the library at every launch: 24x0 = k_run_lean, 24x1 = the general k_run)
+   are run in alternating blocks of `steps`
    launches so that power-cap clock drift hits all of them alike.
    python tools/ab.py 24x0,24x1 [k] [rounds] [steps] [points]"""
 import os, sys, statistics

@@ -20,7 +20,7 @@ for k in (3, 24):
     for key, v in bench.par_dict("slater", k).items():
         setattr(par, key, v)
     par.tsticsub = par.tstic / k
-    for shape in (os.environ.get("TUNE_SHAPES", "24x0,24x1,20x0").split(",")):
+    for shape in (os.environ.get("TUNE_SHAPES", "24x0,24x1").split(",")):
         os.environ["SEMIC_SHAPE"] = shape
         engine.run(st, par, bnd, forcing, 8, out=out, out_days=8)
         ts = [engine.run(st, par, bnd, forcing, days, out=out, out_days=days) for _ in range(3)]
