@@ -228,6 +228,17 @@ def main():
         torch.cuda.set_device(local_rank)
         dist.init_process_group("nccl")
 
+    # one rank per GPU: run on the CPUs next to it, so that the pinned host buffers of the end-to-end leg are
+    # allocated on the GPU's own NUMA node (first touch) and the PCIe copies do not cross the socket interconnect
+    numa = "unbound"
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        pynvml.nvmlDeviceSetCpuAffinity(pynvml.nvmlDeviceGetHandleByIndex(local_rank))
+        numa = "cpus %s" % (sorted(os.sched_getaffinity(0))[:1] + sorted(os.sched_getaffinity(0))[-1:])
+    except Exception as e:                                                    # affinity is an optimisation, never a failure
+        numa = "unbound (%s)" % str(e)[:60]
+
     from semic_b200 import engine
     from semic_b200 import surface_physics as sp
     from semic_b200._capi import FIELD_ID, check, lib
@@ -325,7 +336,7 @@ def main():
         e2e = {"value": float(N) * world * args.e2e_days * args.e2e_steps / (tot * 1e-3), "unit": "point-days/s",
                "h2d_bytes_per_step": int(N) * args.e2e_days * B_FORCING * world,
                "d2h_bytes_per_step": int(N) * args.e2e_days * B_OUT * world,
-               "days_per_step": args.e2e_days, "steps": args.e2e_steps,
+               "days_per_step": args.e2e_days, "steps": args.e2e_steps, "rank0_cpu_affinity": numa,
                "api": "semic_run_host (pinned host forcing window -> H2D || kernel || D2H of the 8 daily fields, pipelined in units of 1 day x 4 Mi points; PCIe bound: 72 B in + 64 B out per point-day)"}
         hf.free()
         ho.free()
@@ -421,6 +432,10 @@ def main():
         line["extra"] = extra
 
     if not args.no_cpu:
+        try:                                                                  # the CPU arm gets every host core back
+            os.sched_setaffinity(0, range(os.cpu_count() or 1))
+        except Exception:
+            pass
         r, cores, sec = cpu_reference_rate(args.scheme, args.n_ksub, args.cpu_points_per_core, args.cpu_days, 2)
         line["cpu_baseline"] = {"value": r, "unit": "point-days/s", "cores": cores, "kind": "port",
                                 "sample": "%d cores x %d points x %d days, best of 2 (array-form C oracle of surface_physics.f90, "
