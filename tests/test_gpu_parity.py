@@ -569,6 +569,41 @@ def test_ensemble_cost_matches_oracle():
     assert err <= 1e-9          # one-pass shifted sums on the device vs the reference's two-pass CRMSD
 
 
+@pytest.mark.parametrize("case", ["same_scheme_mixed_k", "mixed_scheme_k3", "mixed_both"])
+def test_ensemble_with_mixed_schemes_and_substeps(case):
+    """particles that differ in alb_scheme and/or n_ksub take the run-time instantiations of the ensemble kernel"""
+    from semic_b200 import engine
+    from semic_b200 import surface_physics as spm
+    from tests.test_dist_gloo import _oracle_partials
+    g = _gpu()
+    nx, ntime, nloop = 150, 70, 1
+    mask = np.full(nx, 2, dtype=np.int32)
+    mask[::5] = 1
+    forc, vali, names, pop, init = _ensemble_case(nx, ntime, mask)
+    schemes = {"same_scheme_mixed_k": ["none"] * 6, "mixed_scheme_k3": ["none", "slater", "isba", "denby", "alex", "slater"],
+               "mixed_both": ["slater", "none", "isba", "denby", "alex", "xyz"]}[case]
+    ks = {"same_scheme_mixed_k": [3, 2, 5, 3, 4, 3], "mixed_scheme_k3": [3] * 6, "mixed_both": [3, 4, 2, 3, 6, 3]}[case]
+    pars = []
+    for sch, k in zip(schemes, ks):
+        d = dict(util.SCHEME_PARS.get(sch, util.PAR_SLATER), n_ksub=k)
+        d["alb_scheme"] = sch
+        pars.append(g.make_par(d))
+    st = spm.Surface_State_Class()
+    spm.surface_alloc(st, nx)
+    st.mask = mask
+    for k, v in init.items():
+        setattr(st, k, v)
+    st.upload()
+    fs = engine.Series(nx, 9, ntime).upload(forc)
+    vs = engine.Series(nx, 8, ntime).upload(vali)
+    sumsq, _ = engine.ensemble_cost(st, pars, spm.Boundary_Opt_Class(), fs, vs, ntime, nloop)
+    ref = _oracle_partials(pars, forc, vali, mask, init, ntime, nloop)
+    fs.free(); vs.free(); spm.surface_dealloc(st)
+    err = np.max(np.abs(sumsq - ref) / ref)
+    print("\n[ensemble %s] max rel error of the sums of squared CRMSDs %.3e" % (case, err))
+    assert err <= 1e-9
+
+
 def test_ensemble_with_nccl_communicator_single_rank():
     """the library's own NCCL plumbing (unique id -> comm init -> in-place all-reduce) on a 1-rank communicator"""
     import ctypes as C
