@@ -422,9 +422,13 @@ DEVI void energy_substeps(double &ts, double &t2m, double &shf, double &lhf, dou
         // the diagnostics shf, lhf, lwu of the last sub-step are formed after the loop from d, q, latent heat and ts^4
         double d = 0.0, q = 0.0, lat = 0.0, t4 = 0.0;
         bool ice = false;
+        // ts < t0 and ts_raw > t0 as signed 64-bit integer compares of the bit patterns: identical to the floating-point
+        // compares for every non-NaN ts (t0 > 0), and they run on the ALU pipe in the shadow of the FP64 pipe, which is the
+        // busy one (DSETP costs it two cycles per warp, profiles/r01_summary.md section 4)
+        const long long t0_bits = __double_as_longlong(t0);
 #pragma unroll UNR
         for (int k = 0; k < nsub; ++k) {
-            ice = ts < t0;                                                     // :415
+            ice = __double_as_longlong(ts) < t0_bits;                          // :415
             q = latent_q<ALLG>(ts, lat_a, lat_b, sp, ice, tab);                // :179-185
             lat = ice ? kc[22] : kc[23];
             d = ts - t2m;                                                      // :173
@@ -434,7 +438,7 @@ DEVI void energy_substeps(double &ts, double &t2m, double &shf, double &lhf, dou
             const double qsb = fma(-shf_c, d, fma(-sigm, t4, radq)) - lh;      // :194
             ts_raw = fma(qsb, c, ts);                                          // :199
             if (gate) t2m = fma(fma(shf_c, d, lh), c, t2m);                    // :209-211 (Q1: forcing t2m is mutated)
-            ts = (gate && ts_raw > t0) ? t0 : ts_raw;                          // :201-204; the excess is formed below
+            ts = (gate && __double_as_longlong(ts_raw) > t0_bits) ? t0 : ts_raw;   // :201-204; the excess is formed below
         }
         if (nsub > 0) {
             shf = shf_c * d;
