@@ -137,6 +137,42 @@ def test_lean_kernel_parity(scheme, k):
     assert same
 
 
+def test_lean_kernel_random_shapes_against_the_bitmap_kernel():
+    """shell logic of k_run_lean (tile walk, window wrap, first written day, ragged tail, ring stages across tiles):
+    random small shapes must reproduce k_run (selected by the 9-row output) bit for bit"""
+    from semic_b200 import engine
+    from semic_b200 import surface_physics as spm
+    g = _gpu()
+    r = np.random.default_rng(2026)
+    for case in range(24):
+        nx = int(r.choice([1, 5, 31, 32, 33, 64, 100, 777, 1024, 1025, 5000, 24 * 148 * 32 + 7]))
+        nwin = int(r.integers(1, 9))
+        ndays = int(r.integers(1, 23))
+        out_days = int(r.integers(0, ndays + 1))
+        day0 = int(r.integers(0, 3 * nwin))
+        k = int(r.choice([1, 2, 3, 3, 3, 8]))
+        scheme = str(r.choice(["slater", "none", "isba"]))
+        forc = util.random_forcing(nx, nwin, seed=100 + case)
+        mask = r.choice(np.array([2, 1, 0], dtype=np.int32), size=nx, p=[0.8, 0.15, 0.05]).astype(np.int32)
+        S0, m0 = util.init_slab(nx, mask)
+        par, bnd = g.make_par(dict(util.SCHEME_PARS[scheme], n_ksub=k)), g.make_bnd()
+        res = []
+        for nrow in (8, 9):                                             # 8 rows: k_run_lean, 9 rows: k_run + bitmap
+            st = g.make_state(S0, m0)
+            fs = engine.Series(nx, 9, nwin).upload(forc)
+            outs = engine.Series(nx, nrow, max(out_days, 1))
+            engine.run(st, par, bnd, fs, ndays, day0=day0, out=outs if out_days else None, out_days=out_days)
+            st.download()
+            o = outs.download()[:out_days, :8, :] if out_days else None
+            res.append((st.as_slab()[:23].copy(), o))
+            spm.surface_dealloc(st)
+            fs.free(); outs.free()
+        tag = (case, nx, nwin, ndays, out_days, day0, k, scheme)
+        assert np.array_equal(res[0][0], res[1][0]), tag
+        if out_days:
+            assert np.array_equal(res[0][1], res[1][1]), tag
+
+
 def test_lean_kernel_output_ring_and_chunks():
     """daily output into a ring shorter than the run keeps the last days; a run cut into launches continues bit for bit"""
     from semic_b200 import engine
