@@ -368,10 +368,12 @@ struct Pt {
 };
 
 #define BND(x) (GENERIC && (B.x != 0))
+// tsurf and alb overrides are also honoured by the EXT2 instantiations of the plain path (k_run_lean with external rows)
+#define BNDX(x) ((GENERIC || EXT2) && (B.x != 0))
 
 // n_ksub x energy_balance (surface_physics.f90:158-214) for one point; state in registers
 #if SEMIC_STRICT
-template <bool GENERIC, bool ALLG, int UNR>
+template <bool GENERIC, bool ALLG, int UNR, bool EXT2 = false>
 DEVI void energy_substeps(double &ts, double &t2m, double &shf, double &lhf, double &subl, double &evap, double &lwu,
                           double &q_last, double &over, bool &ice_last, const double shf_c, const double lhf_c,
                           const double rad, const double qq, const double sp, const double qmr_res, const bool gate,
@@ -393,7 +395,7 @@ DEVI void energy_substeps(double &ts, double &t2m, double &shf, double &lhf, dou
         lwu = longwave_upward(ts, c_sigm);                                     // :191
         const double qsb = (((rad - lwu) - shf) - lhf) - qmr_res;              // :194
         over = 0.0;                                                            // :197
-        if (!BND(tsurf)) {                                                     // :198
+        if (!BNDX(tsurf)) {                                                    // :198
             ts = ts + fdiv(qsb * P.tsticsub, P.ceff);                          // :199
             if (gate && ts > c_t0) {                                           // :201-204
                 over = ts - c_t0;
@@ -407,7 +409,7 @@ DEVI void energy_substeps(double &ts, double &t2m, double &shf, double &lhf, dou
 // Fast arithmetic.  This translation unit is compiled with -fmad=false: every fused operation below is written as
 // fma(), so all instantiations (unroll factors, compile-time n_ksub, bitmap or not) produce the same bits.
 // ALLG: every lane of the warp is gated (mask == 2 or snow covered) with ts <= t0; a compile-time true removes selects.
-template <bool GENERIC, bool ALLG, int UNR>
+template <bool GENERIC, bool ALLG, int UNR, bool EXT2 = false>
 DEVI void energy_substeps(double &ts, double &t2m, double &shf, double &lhf, double &subl, double &evap, double &lwu,
                           double &q_last, double &over, bool &ice_last, const double shf_c, const double lhf_c,
                           const double rad, const double qq, const double sp, const double qmr_res, const bool gate_in,
@@ -436,9 +438,11 @@ DEVI void energy_substeps(double &ts, double &t2m, double &shf, double &lhf, dou
             t4 = t2 * t2;                                                      // :191
             const double lh = lat * q;
             const double qsb = fma(-shf_c, d, fma(-sigm, t4, radq)) - lh;      // :194
-            ts_raw = fma(qsb, c, ts);                                          // :199
             if (gate) t2m = fma(fma(shf_c, d, lh), c, t2m);                    // :209-211 (Q1: forcing t2m is mutated)
-            ts = (gate && __double_as_longlong(ts_raw) > t0_bits) ? t0 : ts_raw;   // :201-204; the excess is formed below
+            if (!BNDX(tsurf)) {                                                // :198 (external tsurf stays as given)
+                ts_raw = fma(qsb, c, ts);                                      // :199
+                ts = (gate && __double_as_longlong(ts_raw) > t0_bits) ? t0 : ts_raw;   // :201-204; the excess is formed below
+            }
         }
         if (nsub > 0) {
             shf = shf_c * d;
@@ -448,30 +452,44 @@ DEVI void energy_substeps(double &ts, double &t2m, double &shf, double &lhf, dou
             ice_last = ice;
         }
     } else {
+        // all boundary flags; the same fused forms as above wherever the flag set allows, so that a run whose flags are
+        // a subset of {tsurf, alb} gives the same bits here and in the EXT2 instantiation of the plain path
 #pragma unroll UNR
         for (int k = 0; k < nsub; ++k) {
-            if (!BND(shf)) shf = shf_c * (ts - t2m);                           // :173
+            double lh = lhf;
             if (!BND(lhf)) {                                                   // :179-185
                 const bool ice = ts < t0;
                 const double q = latent_q<false>(ts, lat_a, lat_b, sp, ice, tab);
-                lhf = q * (ice ? kc[22] : kc[23]);
+                lh = (ice ? kc[22] : kc[23]) * q;
+                lhf = lh;
                 q_last = q;
                 ice_last = ice;
                 subl = ice ? q : 0.0;
                 evap = ice ? 0.0 : q;
             }
             subl = fdiv(subl, c_rhow);                                         // :186 (every sub-step, Q3)
-            lwu = longwave_upward(ts, sigm);                                   // :191
-            const double qsb = ((radq - lwu) - shf) - lhf;                     // :194
-            if (!BND(tsurf)) {
+            const double t2 = ts * ts;
+            const double t4 = t2 * t2;
+            lwu = sigm * t4;                                                   // :191
+            double qsb, sl;
+            if (!BND(shf)) {
+                const double d = ts - t2m;                                     // :173
+                shf = shf_c * d;
+                qsb = fma(-shf_c, d, fma(-sigm, t4, radq)) - lh;               // :194
+                sl = fma(shf_c, d, lh);
+            } else {
+                qsb = (fma(-sigm, t4, radq) - shf) - lh;
+                sl = shf + lh;
+            }
+            if (gate) t2m = fma(sl, c, t2m);                                   // :209-211
+            if (!BNDX(tsurf)) {                                                // :198-204
                 ts_raw = fma(qsb, c, ts);
                 ts = (gate && ts_raw > t0) ? t0 : ts_raw;
             }
-            if (gate) t2m = fma(shf + lhf, c, t2m);
         }
     }
     // only the last sub-step's excess survives (:197, Q2)
-    if (nsub > 0) over = (!BND(tsurf) && gate && ts_raw > t0) ? ts_raw - t0 : 0.0;
+    if (nsub > 0) over = (!BNDX(tsurf) && gate && ts_raw > t0) ? ts_raw - t0 : 0.0;
 }
 #endif
 
@@ -480,7 +498,7 @@ DEVI void energy_substeps(double &ts, double &t2m, double &shf, double &lhf, dou
 // memory in k_ensemble): variable v is row[v*T].  Values are read where they are first needed (LDS
 // is cheap, registers across the sub-step loop are not); `swd_out` returns the day's shortwave for
 // the swnet diagnostic.
-template <int SCHEME, bool GENERIC, bool WANT_BRANCH, int UNR = 2, int NK = 0>
+template <int SCHEME, bool GENERIC, bool WANT_BRANCH, int UNR = 2, int NK = 0, bool EXT2 = false>
 DEVI unsigned point_day(Pt &s, const double *row, const long long T, const DevPar &P, const semic_bnd &B,
                         const int eb_steps, const int do_mb, double &swd_out, const double *tab)
 {
@@ -515,10 +533,10 @@ DEVI unsigned point_day(Pt &s, const double *row, const long long T, const DevPa
         // every active lane of the warp is gated, e.g. the interior of an ice sheet
         const bool allg = !GENERIC && !SEMIC_STRICT && __all_sync(__activemask(), gate && ts <= c_t0);
         if (allg)
-            energy_substeps<GENERIC, true, UNR>(ts, t2m, shf, lhf, subl, evap, lwu, q_last, over, ice_last, shf_c, lhf_c, rad,
+            energy_substeps<GENERIC, true, UNR, EXT2>(ts, t2m, shf, lhf, subl, evap, lwu, q_last, over, ice_last, shf_c, lhf_c, rad,
                                                 qq, sp, s.qmr_res, gate, nsub, P, B, tab);
         else
-            energy_substeps<GENERIC, false, UNR>(ts, t2m, shf, lhf, subl, evap, lwu, q_last, over, ice_last, shf_c, lhf_c, rad,
+            energy_substeps<GENERIC, false, UNR, EXT2>(ts, t2m, shf, lhf, subl, evap, lwu, q_last, over, ice_last, shf_c, lhf_c, rad,
                                                  qq, sp, s.qmr_res, gate, nsub, P, B, tab);
         if (any) {
             // only the last sub-step's qmr survives (:197, Q2)
@@ -655,7 +673,7 @@ DEVI unsigned point_day(Pt &s, const double *row, const long long T, const DevPa
         if (WANT_BRANCH) { if (hsnow == 0.0) branch |= SEMIC_B_HSNOW_ZERO; }
         if (WANT_BRANCH) { if (snow_to_ice > 0.0) branch |= SEMIC_B_SNOW2ICE; }
 
-        if (!BND(alb)) {                                                           // :339 (Q6: the whole block is skipped)
+        if (!BNDX(alb)) {                                                          // :339 (Q6: the whole block is skipped)
 #if SEMIC_STRICT
             const double f_alb = 1.0 - fexp(fdiv(-hsnow, P.hcrit_eps));            // :338
 #else
@@ -978,12 +996,25 @@ DEVI bool elect_one()
 // AVG: instead of every day's 8 fields, their means over consecutive periods of a.avg_days days are written (the
 // surface_physics_average protocol, surface_physics.f90:565-629: zero at 'init', add at every 'step', divide by the
 // number of steps at 'end'), accumulated in registers: the daily 64 B/point of output traffic become 64/avg_days.
-template <int SCHEME, int WPC, int UNR, int NK, bool AVG = false>
+// EXT: bnd%tsurf and/or bnd%alb with an external series (BASELINE configs[3]; example.f90:103-104): the day's rows
+// stt / alb of the validation-layout series ride in the same stage as the forcing (one more bulk copy of 256 or 512 B).
+template <int WPC, bool EXT>
+struct LeanSmem {
+    static constexpr int ROWS = kForcingRows + (EXT ? 2 : 0);
+    static constexpr int STAGES = kStages;
+    static constexpr size_t stage_bytes = (size_t)ROWS * kTile * sizeof(double);           // 2304 B (2816 B with external rows)
+    static constexpr size_t ring_bytes = stage_bytes * STAGES * WPC;
+    static constexpr size_t bar_bytes = (size_t)WPC * STAGES * sizeof(uint64_t);
+    static constexpr size_t bytes = ring_bytes + bar_bytes + kExpTab * sizeof(double);      // rings, barriers, exp table
+};
+
+template <int SCHEME, int WPC, int UNR, int NK, bool AVG = false, bool EXT = false>
 __global__ void __launch_bounds__(WPC * 32, 1) k_run_lean(const __grid_constant__ RunArgs a)
 {
-    using SM = RunSmem<false, WPC>;
+    using SM = LeanSmem<WPC, EXT>;
     constexpr int NST = SM::STAGES;
     constexpr uint32_t SB = (uint32_t)SM::stage_bytes;
+    constexpr uint32_t FB = (uint32_t)(kForcingRows * kTile * sizeof(double));   // forcing bytes per tile-day
     constexpr int FBLK = kForcingRows * kTile;                   // doubles per tile-day of forcing
     constexpr int OBLK = SEMIC_NOUT * kTile;                     // doubles per tile-day of output
     extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -1013,22 +1044,32 @@ __global__ void __launch_bounds__(WPC * 32, 1) k_run_lean(const __grid_constant_
     int ostart = (a.out != nullptr) ? a.out_start : ndays;       // first day that is written
     asm volatile("" : "+r"(ostart));                             // keep it in a register instead of re-deriving it daily
     uint32_t stage = 0, phase = 0;
+    // external rows: stt (row 0) and alb (row 1) of the validation layout are adjacent: one copy covers what is flagged
+    const bool x_ts = EXT && a.B.tsurf != 0, x_alb = EXT && a.B.alb != 0;
+    const int x_row0 = x_ts ? SEMIC_O_STT : SEMIC_O_ALB;
+    const uint32_t x_bytes = EXT ? (uint32_t)((x_ts ? 1 : 0) + (x_alb ? 1 : 0)) * kTile * (uint32_t)sizeof(double) : 0u;
+    const uint32_t x_dst = FB + (uint32_t)x_row0 * kTile * (uint32_t)sizeof(double);       // stage rows 9 (stt), 10 (alb)
+    const long long v_day = ntl * OBLK;                          // doubles per day of the external series
 
     for (long long tile = (long long)blockIdx.x * WPC + warp; tile < ntiles; tile += nwarps) {
         const double *ftile = a.forcing + tile * FBLK;
         int fd = a.f_day0 % a.f_nwin;                            // next forcing day to fetch and its address
         const double *fsrc = ftile + (long long)fd * f_day;
+        const double *vtile = EXT ? a.vali + tile * OBLK + (long long)x_row0 * kTile : nullptr;
+        const double *vsrc = EXT ? vtile + (long long)fd * v_day : nullptr;
         int d_issue = 0;
         {
             uint32_t s = stage;
             const int npre = ndays < NST ? ndays : NST;
             for (; d_issue < npre; ++d_issue) {
                 if (elect_one()) {
-                    mbar_expect_tx(bar_u + 8u * s, SB);
-                    tma_load_1d(ring_u + s * SB, fsrc, SB, bar_u + 8u * s);
+                    mbar_expect_tx(bar_u + 8u * s, FB + x_bytes);
+                    tma_load_1d(ring_u + s * SB, fsrc, FB, bar_u + 8u * s);
+                    if (EXT) tma_load_1d(ring_u + s * SB + x_dst, vsrc, x_bytes, bar_u + 8u * s);
                 }
                 fsrc += f_day;
-                if (++fd == a.f_nwin) { fd = 0; fsrc = ftile; }
+                if (EXT) vsrc += v_day;
+                if (++fd == a.f_nwin) { fd = 0; fsrc = ftile; if (EXT) vsrc = vtile; }
                 if (++s == NST) s = 0;
             }
         }
@@ -1059,8 +1100,12 @@ __global__ void __launch_bounds__(WPC * 32, 1) k_run_lean(const __grid_constant_
         for (int d = 0; d < ndays; ++d) {
             mbar_wait(bar_u + 8u * stage, phase);
             const double *row = ring + (size_t)stage * (SB / sizeof(double));
+            if (EXT) {                                           // example.f90:103-104
+                if (x_ts)  s.tsurf = row[(kForcingRows + SEMIC_O_STT) * kTile];
+                if (x_alb) s.alb   = row[(kForcingRows + SEMIC_O_ALB) * kTile];
+            }
             double swd;
-            point_day<SCHEME, false, false, UNR, NK>(s, row, kTile, a.P, a.B, 0, 1, swd, tab);
+            point_day<SCHEME, false, false, UNR, NK, EXT>(s, row, kTile, a.P, a.B, 0, 1, swd, tab);
             if (d >= ostart) {                                   // example.f90:117-122
                 if (!AVG) {
                     oday[SEMIC_O_STT * kTile]   = s.tsurf;
@@ -1123,12 +1168,14 @@ __global__ void __launch_bounds__(WPC * 32, 1) k_run_lean(const __grid_constant_
             __syncwarp();
             if (d_issue < ndays) {
                 if (elect_one()) {
-                    mbar_expect_tx(bar_u + 8u * stage, SB);
-                    tma_load_1d(ring_u + stage * SB, fsrc, SB, bar_u + 8u * stage);
+                    mbar_expect_tx(bar_u + 8u * stage, FB + x_bytes);
+                    tma_load_1d(ring_u + stage * SB, fsrc, FB, bar_u + 8u * stage);
+                    if (EXT) tma_load_1d(ring_u + stage * SB + x_dst, vsrc, x_bytes, bar_u + 8u * stage);
                 }
                 ++d_issue;
                 fsrc += f_day;
-                if (++fd == a.f_nwin) { fd = 0; fsrc = ftile; }
+                if (EXT) vsrc += v_day;
+                if (++fd == a.f_nwin) { fd = 0; fsrc = ftile; if (EXT) vsrc = vtile; }
             }
             if (++stage == NST) { stage = 0; phase ^= 1u; }
         }
@@ -1257,6 +1304,7 @@ __global__ void k_ens_reduce(const double *partial, int ntiles, int npar, double
 #endif  // !SEMIC_STRICT
 
 #undef BND
+#undef BNDX
 
 }  // namespace SEMIC_MODE_NS
 }  // namespace semic

@@ -60,15 +60,22 @@ cudaError_t launch_run_fast(const RunArgs &a, bool generic, cudaStream_t st, int
 {
     if (launches) ++*launches;
     if (cudaError_t e = ensure_exp_table()) return e;
-    if (generic) return fast_mode::launch_scheme<true, 1, 8>(a, st);
-    // Plain runs go to k_run_lean; what it does not cover (the bitmap row, the drop-in single day on the slab's own
-    // forcing fields, n_ksub < 1) runs k_run.  SEMIC_SHAPE=24x1 forces k_run for A/B timing (tools/ab.py).
     const char *e = getenv("SEMIC_SHAPE");
     const bool force_general = e && std::strcmp(e, "24x1") == 0;
     const bool lean_ok = a.f_tiled && a.ndays >= 1 && a.P.n_ksub >= 1 && (a.out == nullptr || a.o_nvar == SEMIC_NOUT);
     const bool want_avg = a.out != nullptr && a.avg_days > 1;
+    if (generic) {
+        // BASELINE configs[3]: only tsurf and/or alb are overridden, from an external series -> the plain path with two
+        // more rows per stage; every other flag set runs the general kernel (all 23 fields carried)
+        const semic_bnd &B = a.B;
+        const bool only_ts_alb = (B.tsurf || B.alb) && !(B.shf || B.lhf || B.amp || B.melt || B.refr || B.acc || B.smb);
+        if (only_ts_alb && a.vali != nullptr && lean_ok && !want_avg && !force_general) return fast_mode::launch_lean(a, st, true);
+        return fast_mode::launch_scheme<true, 1, 8>(a, st);
+    }
+    // Plain runs go to k_run_lean; what it does not cover (the bitmap row, the drop-in single day on the slab's own
+    // forcing fields, n_ksub < 1) runs k_run.  SEMIC_SHAPE=24x1 forces k_run for A/B timing (tools/ab.py).
     if (want_avg && !lean_ok) return cudaErrorNotSupported;                  // period means: plain runs only
-    if (lean_ok && (want_avg || !force_general)) return fast_mode::launch_lean(a, st);
+    if (lean_ok && (want_avg || !force_general)) return fast_mode::launch_lean(a, st, false);
     return a.P.n_ksub >= 8 ? fast_mode::launch_scheme<false, 1, 24, 4>(a, st) : fast_mode::launch_scheme<false, 1, 24, 2>(a, st);
 }
 

@@ -42,11 +42,11 @@ static cudaError_t launch_scheme(const RunArgs &a, cudaStream_t st)
 
 #if !SEMIC_STRICT
 // k_run_lean: the plain (no boundary flag) tiled-forcing run with 8 daily rows, n_ksub >= 1
-template <int SCHEME, int WPC, int UNR, int NK, bool AVG>
+template <int SCHEME, int WPC, int UNR, int NK, bool AVG, bool EXT>
 static cudaError_t launch_lean_one(const RunArgs &a, cudaStream_t st)
 {
-    auto kern = k_run_lean<SCHEME, WPC, UNR, NK, AVG>;
-    constexpr size_t smem = RunSmem<false, WPC>::bytes;
+    auto kern = k_run_lean<SCHEME, WPC, UNR, NK, AVG, EXT>;
+    constexpr size_t smem = LeanSmem<WPC, EXT>::bytes;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     int dev = 0, nsm = 0;
@@ -61,24 +61,28 @@ static cudaError_t launch_lean_one(const RunArgs &a, cudaStream_t st)
     return cudaGetLastError();
 }
 
-template <int WPC, int UNR, int NK, bool AVG>
+template <int WPC, int UNR, int NK, bool AVG, bool EXT = false>
 static cudaError_t launch_lean_nk(const RunArgs &a, cudaStream_t st)
 {
     switch (a.P.scheme) {
-        case SCHEME_NONE:   return launch_lean_one<SCHEME_NONE, WPC, UNR, NK, AVG>(a, st);
-        case SCHEME_SLATER: return launch_lean_one<SCHEME_SLATER, WPC, UNR, NK, AVG>(a, st);
-        case SCHEME_DENBY:  return launch_lean_one<SCHEME_DENBY, WPC, UNR, NK, AVG>(a, st);
-        case SCHEME_ISBA:   return launch_lean_one<SCHEME_ISBA, WPC, UNR, NK, AVG>(a, st);
-        case SCHEME_ALEX:   return launch_lean_one<SCHEME_ALEX, WPC, UNR, NK, AVG>(a, st);
-        default:            return launch_lean_one<SCHEME_UNKNOWN, WPC, UNR, NK, AVG>(a, st);
+        case SCHEME_NONE:   return launch_lean_one<SCHEME_NONE, WPC, UNR, NK, AVG, EXT>(a, st);
+        case SCHEME_SLATER: return launch_lean_one<SCHEME_SLATER, WPC, UNR, NK, AVG, EXT>(a, st);
+        case SCHEME_DENBY:  return launch_lean_one<SCHEME_DENBY, WPC, UNR, NK, AVG, EXT>(a, st);
+        case SCHEME_ISBA:   return launch_lean_one<SCHEME_ISBA, WPC, UNR, NK, AVG, EXT>(a, st);
+        case SCHEME_ALEX:   return launch_lean_one<SCHEME_ALEX, WPC, UNR, NK, AVG, EXT>(a, st);
+        default:            return launch_lean_one<SCHEME_UNKNOWN, WPC, UNR, NK, AVG, EXT>(a, st);
     }
 }
 
 // n_ksub = 3 (every shipped namelist: example.namelist:30, optimization.namelist, tools.py:31) is a compile-time
 // constant of its own instantiation: the three sub-steps share one set of constant loads.
 // Daily output: 24 warps x 80 registers.  Period means (8 accumulators more per thread): 20 warps x 96 registers.
-static cudaError_t launch_lean(const RunArgs &a, cudaStream_t st)
+static cudaError_t launch_lean(const RunArgs &a, cudaStream_t st, bool ext)
 {
+    if (ext) {                                   // external tsurf / alb rows: daily output only
+        if (a.P.n_ksub == 3) return launch_lean_nk<24, 3, 3, false, true>(a, st);
+        return launch_lean_nk<24, 2, 0, false, true>(a, st);
+    }
     if (a.out != nullptr && a.avg_days > 1) {
         if (a.P.n_ksub == 3) return launch_lean_nk<20, 3, 3, true>(a, st);
         return launch_lean_nk<20, 2, 0, true>(a, st);

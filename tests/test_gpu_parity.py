@@ -173,6 +173,34 @@ def test_lean_kernel_random_shapes_against_the_bitmap_kernel():
             assert np.array_equal(res[0][1], res[1][1]), tag
 
 
+@pytest.mark.parametrize("names", [("tsurf",), ("alb",), ("tsurf", "alb")])
+@pytest.mark.parametrize("k", [3, 4])
+def test_lean_kernel_with_external_tsurf_and_alb(names, k):
+    """BASELINE configs[3]: isba with bnd%tsurf / bnd%alb fed from an external series runs the plain path with two more
+    rows per stage; bit-identical to the general kernel (9-row run) and within 1e-10 of the oracle"""
+    from semic_b200 import engine
+    g = _gpu()
+    nx, nwin, ndays = 1024 + 99, 40, 150
+    forc = util.random_forcing(nx, nwin, seed=21)
+    r = np.random.default_rng(5)
+    mask = r.choice(np.array([2, 1, 0], dtype=np.int32), size=nx, p=[0.85, 0.10, 0.05]).astype(np.int32)
+    S0, m0 = util.init_slab(nx, mask)
+    par = dict(util.PAR_ISBA, n_ksub=k)
+    # external series: a plain run's own daily output over the window (tsurf <= t0 over snow, alb in [0, 1])
+    _, ext, _, _ = g.run_gpu(S0, m0, par, (), forc, nwin, out_days=nwin, branch=False)
+    ext = np.ascontiguousarray(ext)
+    fin_l, out_l, _, _ = g.run_gpu(S0, m0, par, names, forc, ndays, vali=ext, out_days=ndays, branch=False)   # k_run_lean<EXT>
+    fin_b, out_b, br_b, _ = g.run_gpu(S0, m0, par, names, forc, ndays, vali=ext, out_days=ndays, branch=True)  # k_run<GENERIC>
+    fin_o, out_o, br_o = g.run_oracle(S0, m0, par, names, forc, ndays, vali=ext, out_days=ndays)
+    assert np.array_equal(out_l, out_b) and np.array_equal(fin_l[:23], fin_b[:23])
+    taint = util.tainted(br_b, br_o)
+    oe = util.out_errors(out_l, out_o, exclude=taint)
+    se = util.state_errors(fin_l, fin_o, exclude_points=taint.any(axis=0))
+    print("\n[lean ext %s k=%d] daily %.2e state %.2e tainted points %d" % ("+".join(names), k, max(oe.values()),
+                                                                            max(se.values()), int(taint.any(axis=0).sum())))
+    assert max(oe.values()) <= TOL and max(se.values()) <= TOL
+
+
 def test_lean_kernel_output_ring_and_chunks():
     """daily output into a ring shorter than the run keeps the last days; a run cut into launches continues bit for bit"""
     from semic_b200 import engine
