@@ -399,6 +399,32 @@ def main():
             means.free()
         except Exception as e:
             extra["C3_monthly_means_error"] = str(e)[:200]
+        # the big C3 buffers are done: release them before the other configurations allocate theirs
+        forcing.free()
+        out.free()
+        sp.surface_dealloc(st)
+        # C4 (configs[3]): isba with surface_boundary_define overrides from an external series, 4 194 304 points, n_ksub=3
+        try:
+            n4 = 1 << 22
+            st4 = make_state(n4, 0)
+            f4 = engine.Series(n4, 9, args.window).synth_forcing(SEED, daystride=args.window_stride)
+            o4 = engine.Series(n4, 8, args.ring)
+            v4 = engine.Series(n4, 8, args.window)
+            par4 = make_par(3, "isba")
+            engine.run(st4, par4, bnd, f4, args.window, out=v4, out_days=args.window)     # external tsurf / alb series
+            for names in ((), ("tsurf",), ("tsurf", "alb")):
+                b4 = sp.Boundary_Opt_Class()
+                sp.surface_boundary_define(b4, list(names))
+                ts = [engine.run(st4, par4, b4, f4, 365, vali=v4 if names else None, out=o4, out_days=365) for _ in range(5)]
+                t = float(np.mean(ts[2:]))
+                key = "C4_isba_4M_points_%s" % ("+".join(names) if names else "no_override")
+                extra[key + "_point_days_per_s"] = n4 * 365.0 / (t * 1e-3)
+                extra[key + "_hbm_frac"] = n4 * 365.0 / (t * 1e-3) * (136 + 8 * len(names)) / 1e9 / float(measured_peaks()[0].get("hbm_gbs", 6650.0))
+            for x in (f4, o4, v4):
+                x.free()
+            sp.surface_dealloc(st4)
+        except Exception as e:
+            extra["C4_error"] = str(e)[:200]
         # C2: 100k points, 1 year, n_ksub=24, Greenland-like mask
         st2 = make_state(100000, 0, 0.85, 0.10)
         f2 = engine.Series(100000, 9, 365).synth_forcing(SEED)
