@@ -1,22 +1,22 @@
-// semic_kernels.cuh -- the SEMIC point-day physics and the persistent multi-day kernel (sm_100a).
+// semic_kernels.cuh -- the SEMIC point-day physics and the persistent multi-day kernels (sm_100a).
 //
-// Included twice: SEMIC_STRICT=0 (semic_kernels_fast.cu, FMA contraction on, reciprocal
-// multiplies, custom exp) and SEMIC_STRICT=1 (semic_kernels_strict.cu, compiled with
-// -fmad=false: the reference's operation order, IEEE division, no contraction; only the libm
-// calls exp/acos/pow/tanh differ from a gfortran build, by the 1-2 ulp of libdevice vs glibc).
+// Included twice, both translation units compiled with -fmad=false:
+//   SEMIC_STRICT=1 (semic_kernels_strict.cu): the reference's operation order, IEEE division, no fused operations; only
+//     the libm calls exp/acos/pow/tanh differ from a gfortran build, by the 1-2 ulp of libdevice vs glibc;
+//   SEMIC_STRICT=0 (semic_kernels_fast.cu, the benchmarked arithmetic): reciprocal multiplies, table-driven exp, one-
+//     polynomial acos, every fused operation written as fma() so that all instantiations round alike.
 //
-// What it replaces: surface_energy_and_mass_balance (surface_physics.f90:138-153), i.e.
-// n_ksub x energy_balance (:158-214) + mass_balance (:232-374) with the elementals (:378-560),
-// fused per grid point so that every point-day costs 9 forcing loads and (optionally) 8 output
-// stores instead of ~47 array sweeps per sub-step.
+// What it replaces: surface_energy_and_mass_balance (surface_physics.f90:138-153), i.e. n_ksub x energy_balance
+// (:158-214) + mass_balance (:232-374) with the elementals (:378-560), fused per grid point so that every point-day
+// costs 9 forcing loads and (optionally) 8 output stores instead of ~47 array sweeps per sub-step.
 //
-// Kernel shape (k_run): persistent CTAs, one per SM slot.  A CTA owns tiles of T = 256*PPT
-// consecutive points and walks each tile through ALL days with the prognostic state
-// (tsurf, hsnow, hice, alb, alb_snow, qmr_res) in registers.  Warp 8 is the producer: one lane
-// issues 1-D TMA bulk copies (cp.async.bulk, SASS UBLKCP) of the 9 forcing rows of the next
-// days into a kStages-deep shared-memory ring guarded by full/empty mbarriers; warps 0-7
-// consume a stage with conflict-free LDS (values are read where first needed), release it, and store the daily
-// diagnostics coalesced.  No tensor cores: nothing here is a contraction.
+// Kernel shape (k_run_lean, k_run): persistent CTAs, one per SM.  Every WARP owns tiles of 32 consecutive points and
+// walks each tile through ALL days with the prognostic state (tsurf, hsnow, hice, alb, alb_snow, qmr_res) in registers.
+// Each warp feeds itself: one elected lane issues a 1-D TMA bulk copy (cp.async.bulk, SASS UBLKCP) of the next day's
+// forcing rows of the tile into the warp's private kStages-deep shared-memory ring, completion on an mbarrier per stage;
+// lanes read their column with conflict-free LDS where first needed, the warp re-arms the stage after __syncwarp, and the
+// daily diagnostics are stored coalesced.  No producer warp, no cross-warp coupling.  No tensor cores: nothing here is a
+// contraction.
 #pragma once
 
 #include <cuda_runtime.h>
