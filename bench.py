@@ -425,6 +425,37 @@ def main():
             sp.surface_dealloc(st4)
         except Exception as e:
             extra["C4_error"] = str(e)[:200]
+        # the reference-facing per-day call itself (surface_energy_and_mass_balance(now, par, bnd, day, year) on a state
+        # whose array components live on the HOST): every call moves fields over PCIe both ways, synchronously
+        try:
+            n6 = 1 << 22
+            st6 = make_state(n6, 0)
+            f6 = engine.Series(n6, 9, 1).synth_forcing(SEED)
+            fh = f6.download()                                                           # [1][9][n6]
+            for v, name in enumerate(("sf", "rf", "swd", "lwd", "wind", "sp", "rhoa", "qq", "t2m")):
+                setattr(st6, name, fh[0, v])
+            par6 = make_par(3, args.scheme)
+            bit = lambda names: sum(1 << FIELD_ID[x] for x in names)
+            modes = {"all_fields": None,
+                     "forcing_up_outputs_down": (bit(("sf", "rf", "swd", "lwd", "wind", "sp", "rhoa", "qq", "t2m")),
+                                                 bit(("tsurf", "alb", "smb", "melt", "acc", "shf", "lhf")))}
+            for label, sync in modes.items():
+                if sync is not None:
+                    st6.set_sync(*sync)
+                for d in range(3):
+                    sp.surface_energy_and_mass_balance(st6, par6, bnd, d + 1, 0)
+                t0 = time.perf_counter()
+                for d in range(10):
+                    sp.surface_energy_and_mass_balance(st6, par6, bnd, d + 1, 0)
+                dt = (time.perf_counter() - t0) / 10
+                extra["daily_call_4M_points_%s_point_days_per_s" % label] = n6 / dt
+            extra["daily_call_note"] = ("surface_energy_and_mass_balance per day on host-resident state: 248 B/point up + 184 B/point "
+                                        "down by default, 72 + 56 B/point with semic_state_set_sync; PCIe bound; upload, kernel and download are pipelined "
+                                        "over 512 Ki-point slices inside the call")
+            f6.free()
+            sp.surface_dealloc(st6)
+        except Exception as e:
+            extra["daily_call_error"] = str(e)[:200]
         # C2: 100k points, 1 year, n_ksub=24, Greenland-like mask
         st2 = make_state(100000, 0, 0.85, 0.10)
         f2 = engine.Series(100000, 9, 365).synth_forcing(SEED)

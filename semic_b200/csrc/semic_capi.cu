@@ -124,6 +124,9 @@ struct semic_state {
     cudaStream_t stream = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     uint64_t up_fields = SEMIC_FIELDS_ALL, down_fields = 0x7FFFFFull;   // download: the 23 non-forcing fields
+    // created on first use by the sliced per-day call (large grids): copy-in / copy-out streams and per-slice events
+    cudaStream_t s_in = nullptr, s_out = nullptr;
+    std::vector<cudaEvent_t> ev_up, ev_done;
 };
 
 struct semic_series {
@@ -362,6 +365,10 @@ extern "C" int semic_surface_dealloc(semic_state *s)
     cudaFreeHost(s->h_mask);
     cudaEventDestroy(s->ev0);
     cudaEventDestroy(s->ev1);
+    for (cudaEvent_t e : s->ev_up) cudaEventDestroy(e);
+    for (cudaEvent_t e : s->ev_done) cudaEventDestroy(e);
+    if (s->s_in) cudaStreamDestroy(s->s_in);
+    if (s->s_out) cudaStreamDestroy(s->s_out);
     cudaStreamDestroy(s->stream);
     delete s;
     return SEMIC_OK;
@@ -486,26 +493,28 @@ extern "C" double *semic_state_field(semic_state *s, int field)
 extern "C" int *semic_state_mask(semic_state *s) { return s ? s->h_mask : nullptr; }
 extern "C" double *semic_state_device_slab(semic_state *s) { return s ? s->d_slab : nullptr; }
 
-static int state_copy(semic_state *s, uint64_t fields, bool up)
+static int state_copy(semic_state *s, uint64_t fields, bool up, int p0 = 0, int np = -1, cudaStream_t st = nullptr)
 {
     CU(cudaSetDevice(s->device));
-    const size_t rowb = (size_t)s->npts * sizeof(double);
+    if (np < 0) np = s->npts;
+    if (!st) st = s->stream;
+    const size_t rowb = (size_t)np * sizeof(double);
     int f = 0;
     while (f < SEMIC_NFIELDS) {                       // coalesce runs of adjacent fields into one copy
         if (!((fields >> f) & 1ull)) { ++f; continue; }
         int g = f;
         while (g + 1 < SEMIC_NFIELDS && ((fields >> (g + 1)) & 1ull)) ++g;
-        const size_t off = (size_t)f * s->ld;
+        const size_t off = (size_t)f * s->ld + p0;
         const size_t nrows = (size_t)(g - f + 1);
         if (up) CU(cudaMemcpy2DAsync(s->d_slab + off, (size_t)s->ld * 8, s->h_slab + off, (size_t)s->ld * 8, rowb, nrows,
-                                     cudaMemcpyHostToDevice, s->stream));
+                                     cudaMemcpyHostToDevice, st));
         else    CU(cudaMemcpy2DAsync(s->h_slab + off, (size_t)s->ld * 8, s->d_slab + off, (size_t)s->ld * 8, rowb, nrows,
-                                     cudaMemcpyDeviceToHost, s->stream));
+                                     cudaMemcpyDeviceToHost, st));
         f = g + 1;
     }
     if ((fields >> SEMIC_F_MASK) & 1ull) {
-        if (up) CU(cudaMemcpyAsync(s->d_mask, s->h_mask, (size_t)s->npts * sizeof(int), cudaMemcpyHostToDevice, s->stream));
-        else    CU(cudaMemcpyAsync(s->h_mask, s->d_mask, (size_t)s->npts * sizeof(int), cudaMemcpyDeviceToHost, s->stream));
+        if (up) CU(cudaMemcpyAsync(s->d_mask + p0, s->h_mask + p0, (size_t)np * sizeof(int), cudaMemcpyHostToDevice, st));
+        else    CU(cudaMemcpyAsync(s->h_mask + p0, s->d_mask + p0, (size_t)np * sizeof(int), cudaMemcpyDeviceToHost, st));
     }
     return SEMIC_OK;
 }
@@ -683,12 +692,13 @@ static int check_par(const semic_par *par, const char *who)
 
 // one fused launch on the state's own slab (forcing = the state's SoA forcing fields)
 static int step_on_slab(semic_state *s, const semic_par *par, const semic_bnd *bnd, int eb_steps, int do_mb, bool whole_step,
-                        int strict)
+                        int strict, int p0 = 0, int np = -1)
 {
     RunArgs a;
     std::memset(&a, 0, sizeof a);
-    a.slab = s->d_slab; a.mask = s->d_mask; a.nx = s->npts; a.ld = s->ld; a.sld = s->ld;
-    a.forcing = s->d_slab;
+    if (np < 0) np = s->npts;
+    a.slab = s->d_slab + p0; a.mask = s->d_mask + p0; a.nx = np; a.ld = s->ld; a.sld = s->ld;
+    a.forcing = s->d_slab + p0;
     a.f_tiled = 0; a.f_nwin = 1; a.f_day0 = 0;
     const int src_field[kForcingRows] = {SEMIC_F_SF, SEMIC_F_RF, SEMIC_F_SWD, SEMIC_F_LWD, SEMIC_F_WIND, SEMIC_F_SP,
                                          SEMIC_F_RHOA, SEMIC_F_QQ, SEMIC_F_T2M};
@@ -712,10 +722,44 @@ static int dropin(semic_state *s, const semic_par *par, const semic_bnd *bnd, in
     if (!s || !bnd) { set_error("%s: null argument", who); return SEMIC_ERR_ARG; }
     CU(cudaSetDevice(s->device));
     if (s->npts == 0) return SEMIC_OK;
-    if ((rc = state_copy(s, s->up_fields, true))) return rc;
-    if ((rc = step_on_slab(s, par, bnd, eb_steps, do_mb, whole, getenv("SEMIC_STRICT") ? 1 : 0))) return rc;
-    if ((rc = state_copy(s, s->down_fields, false))) return rc;
+    const int strict = getenv("SEMIC_STRICT") ? 1 : 0;
+    // Large grids: the points are independent, so the call is pipelined over slices of the grid -- upload of slice
+    // i+1, kernel of slice i and download of slice i-1 run concurrently (PCIe is full duplex): the call costs about
+    // max(bytes up, bytes down) / PCIe bandwidth instead of their sum.
+    int slice = 1 << 19;
+    if (const char *e = getenv("SEMIC_STEP_SLICE")) { const int v = atoi(e); if (v > 0) slice = round_up(v, kLdAlign); }
+    const int nslices = (s->npts + slice - 1) / slice;
+    if (nslices < 2) {
+        if ((rc = state_copy(s, s->up_fields, true))) return rc;
+        if ((rc = step_on_slab(s, par, bnd, eb_steps, do_mb, whole, strict))) return rc;
+        if ((rc = state_copy(s, s->down_fields, false))) return rc;
+        CU(cudaStreamSynchronize(s->stream));
+        return SEMIC_OK;
+    }
+    if (!s->s_in) CU(cudaStreamCreateWithFlags(&s->s_in, cudaStreamNonBlocking));
+    if (!s->s_out) CU(cudaStreamCreateWithFlags(&s->s_out, cudaStreamNonBlocking));
+    while ((int)s->ev_up.size() < nslices) {
+        cudaEvent_t a = nullptr, b = nullptr;
+        CU(cudaEventCreateWithFlags(&a, cudaEventDisableTiming));
+        s->ev_up.push_back(a);
+        CU(cudaEventCreateWithFlags(&b, cudaEventDisableTiming));
+        s->ev_done.push_back(b);
+    }
+    CU(cudaEventRecord(s->ev0, s->stream));                       // work queued on the state's stream so far comes first
+    CU(cudaStreamWaitEvent(s->s_in, s->ev0, 0));
+    for (int i = 0; i < nslices; ++i) {
+        const int p0 = i * slice;
+        const int np = (p0 + slice <= s->npts) ? slice : s->npts - p0;
+        if ((rc = state_copy(s, s->up_fields, true, p0, np, s->s_in))) return rc;
+        CU(cudaEventRecord(s->ev_up[i], s->s_in));
+        CU(cudaStreamWaitEvent(s->stream, s->ev_up[i], 0));
+        if ((rc = step_on_slab(s, par, bnd, eb_steps, do_mb, whole, strict, p0, np))) return rc;
+        CU(cudaEventRecord(s->ev_done[i], s->stream));
+        CU(cudaStreamWaitEvent(s->s_out, s->ev_done[i], 0));
+        if ((rc = state_copy(s, s->down_fields, false, p0, np, s->s_out))) return rc;
+    }
     CU(cudaStreamSynchronize(s->stream));
+    CU(cudaStreamSynchronize(s->s_out));
     return SEMIC_OK;
 }
 

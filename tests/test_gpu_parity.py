@@ -378,6 +378,53 @@ def test_dropin_daily_step_module_api(tmp_path):
     sp.surface_physics.surface_dealloc(state)
 
 
+def test_dropin_daily_step_pipelined_over_point_slices(monkeypatch):
+    """large grids: the per-day call overlaps upload, kernel and download over slices of the grid; same bits as the
+    unsliced call, also with a narrowed sync set and for energy_balance / mass_balance alone"""
+    from semic_b200 import surface_physics as spm
+    from semic_b200._capi import FIELD_ID
+    g = _gpu()
+    nx, ndays = 5000, 12
+    forc = util.random_forcing(nx, ndays, seed=17)
+    r = np.random.default_rng(3)
+    mask = r.choice(np.array([2, 1, 0], dtype=np.int32), size=nx, p=[0.8, 0.15, 0.05]).astype(np.int32)
+    S0, m0 = util.init_slab(nx, mask)
+    par, bnd = g.make_par(dict(util.PAR_SLATER, n_ksub=3)), g.make_bnd()
+    names9 = ["sf", "rf", "swd", "lwd", "wind", "sp", "rhoa", "qq", "t2m"]
+    bit = lambda names: sum(1 << FIELD_ID[x] for x in names)
+
+    def run(slice_pts, narrow):
+        if slice_pts:
+            monkeypatch.setenv("SEMIC_STEP_SLICE", str(slice_pts))
+        else:
+            monkeypatch.setenv("SEMIC_STEP_SLICE", str(1 << 30))
+        st = g.make_state(S0, m0)
+        if narrow:
+            # t2m comes back too: energy_balance mutates it (Q1) and the separate mass_balance call uploads it again
+            st.set_sync(bit(names9), bit(("tsurf", "alb", "smb", "melt", "acc", "shf", "lhf", "t2m")))
+        daily = []
+        for t in range(ndays):
+            for v, n in enumerate(names9):
+                setattr(st, n, forc[t, v, :])
+            if t % 3 == 2:                                                   # the two halves called separately
+                spm.energy_balance(st, par, bnd, t, 0)
+                spm.mass_balance(st, par, bnd, t, 0)
+            else:
+                spm.surface_energy_and_mass_balance(st, par, bnd, t, 0)
+            daily.append(np.stack([np.array(st.tsurf), np.array(st.alb), np.array(st.smb), np.array(st.melt),
+                                   np.array(st.acc), np.array(st.shf), np.array(st.lhf)]))
+        st.download()
+        fin = st.as_slab()[:23].copy()
+        spm.surface_dealloc(st)
+        return np.array(daily), fin
+
+    ref_d, ref_f = run(0, False)
+    for slice_pts, narrow in ((1024, False), (2048, True), (1024, True)):
+        d, f = run(slice_pts, narrow)
+        assert np.array_equal(d, ref_d), (slice_pts, narrow)
+        assert np.array_equal(f, ref_f), (slice_pts, narrow)
+
+
 def test_energy_and_mass_balance_separately():
     """energy_balance / mass_balance are public module procedures (surface_physics.f90:122)."""
     from oracle import binding as ob
