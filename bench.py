@@ -177,10 +177,11 @@ def run_reference_arm(args):
 
 
 def workload_config(args, world):
+    per_gpu = args.points // world if getattr(args, "strong", False) else args.points
     return {"workload": "C3 synthetic Antarctica-scale grid: %d points/GPU x 365 days/step, slater-family scheme '%s', "
                         "n_ksub=%d, daily output M1 (8 fields), forcing window %d days resident in HBM"
-                        % (args.points, args.scheme, args.n_ksub, args.window),
-            "points_per_gpu": args.points, "days_per_step": args.days, "n_ksub": args.n_ksub, "alb_scheme": args.scheme,
+                        % (per_gpu, args.scheme, args.n_ksub, args.window),
+            "points_per_gpu": per_gpu, "days_per_step": args.days, "n_ksub": args.n_ksub, "alb_scheme": args.scheme,
             "forcing_window_days": args.window, "forcing_window_stride_days": args.window_stride, "output_ring_days": args.ring, "output_mode": "M1",
             "sharding": "contiguous point ranges, no communication", "world_size": world,
             "l2": "inputs (forcing window) far larger than the 126 MB L2; every byte is read once per pass",
@@ -209,6 +210,8 @@ def main():
     ap.add_argument("--cpu-points-per-core", type=int, default=65536,
                     help="CPU sample: points per host core (26 MB of state+forcing per core: not cache resident, like the full grid)")
     ap.add_argument("--cpu-days", type=int, default=365)
+    ap.add_argument("--strong", action="store_true",
+                    help="strong scaling: --points is the WHOLE grid, sharded contiguously over the ranks (default: weak, --points per GPU)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--extra", action="store_true", help="(default now; kept for compatibility)")
@@ -267,8 +270,13 @@ def main():
             check(L.semic_state_fill(st.handle, FIELD_ID[name], v))
         return st
 
-    N = args.points
-    p0 = rank * N
+    if args.strong:                                   # contiguous shard [lo, hi) of the one grid (driver.shard_bounds)
+        lo = args.points * rank // world
+        hi = args.points * (rank + 1) // world
+        N, p0 = hi - lo, lo
+    else:
+        N = args.points
+        p0 = rank * N
     par = make_par(args.n_ksub, args.scheme)
     bnd = sp.Boundary_Opt_Class()
     st = make_state(N, p0)
@@ -303,7 +311,8 @@ def main():
         t = torch.tensor([kernel_ms, wall_ms], dtype=torch.float64, device="cuda")
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         kernel_ms, wall_ms = float(t[0]), float(t[1])
-    ptdays_step = float(N) * args.days * world
+    total_points = float(args.points) if args.strong else float(N) * world
+    ptdays_step = total_points * args.days
     value = ptdays_step * args.steps / (kernel_ms * 1e-3)
 
     # ---- end to end: host (pinned) forcing -> H2D -> kernel -> D2H of the daily output, through semic_run_host ----
@@ -375,7 +384,7 @@ def main():
 
     line = {"metric": "grid-point-days/s", "value": value, "unit": "point-days/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": kernel_ms / max(args.steps, 1), "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "scaling": "strong" if args.strong else "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": workload_config(args, world), "roofline": roofline, "gpu_launches": launches,
             "wall_ms_per_step": wall_ms / max(args.steps, 1), "clocks": clocks}
     if e2e is not None:
