@@ -808,3 +808,26 @@ def test_run_particles_x_native_program(tmp_path):
     init = dict(hsnow=1.0, hice=0.0, alb=vali[0, 1, :], tsurf=vali[0, 0, :], alb_snow=vali[0, 1, :])     # run_particles.f90:77-82
     cost = driver.run_particles(pop, names, forc, vali, mask, init, 365, 2)
     assert np.allclose(native, [cost[i] for i in range(5)], rtol=1e-12, atol=0)
+
+
+def test_run_from_binary_files_equals_in_memory_run(tmp_path):
+    """f3: forcing streamed from a binary columnar file through pinned windows, output streamed to a file"""
+    from semic_b200 import io as sio
+    from semic_b200 import surface_physics as spm
+    g = _gpu()
+    nx, nfile, ndays, out_days = 2500, 20, 47, 30
+    forc = util.random_forcing(nx, nfile, seed=31)
+    mask = np.full(nx, 2, dtype=np.int32)
+    mask[::8] = 1
+    S0, m0 = util.init_slab(nx, mask)
+    par_d = dict(util.PAR_SLATER, n_ksub=3)
+    fin_a, out_a, _, _ = g.run_gpu(S0, m0, par_d, (), forc, ndays, out_days=out_days, branch=False)
+    sio.write_series(str(tmp_path / "forcing.bin"), forc)
+    st = g.make_state(S0, m0)
+    ms = sio.run_files(st, g.make_par(par_d), g.make_bnd(), str(tmp_path / "forcing.bin"), ndays,
+                       out_path=str(tmp_path / "out.bin"), out_days=out_days, window_days=7, chunk_days=2)
+    st.download()
+    assert ms > 0
+    assert np.array_equal(st.as_slab()[:23], fin_a[:23])
+    assert np.array_equal(np.asarray(sio.open_series(str(tmp_path / "out.bin"))), out_a)
+    spm.surface_dealloc(st)

@@ -248,3 +248,21 @@ def test_run_particles_x_stops_at_the_first_missing_namelist(tmp_path):
     r = subprocess.run([exe, '"p_"', "0", "3"], cwd=str(d), capture_output=True, text=True)      # no p_000000.nml: nothing to do
     assert r.returncode == 0 and "p_000000.nml' not found, exiting loop" in r.stdout              # run_particles.f90:110-113
     assert "end particle calculation" in r.stdout
+
+
+def test_binary_series_roundtrip_and_ascii_conversion(tmp_path):
+    from semic_b200 import io as sio
+    forc, vali = util.load_fixture("transect")
+    sio.write_series(str(tmp_path / "f.bin"), forc)
+    m = sio.open_series(str(tmp_path / "f.bin"))
+    assert m.shape == forc.shape and np.array_equal(np.asarray(m), forc)
+    np.savetxt(tmp_path / "v.txt", vali.reshape(365, -1))                    # the reference's ASCII layout, utils.f90:89-93
+    sio.ascii_to_binary(str(tmp_path / "v.txt"), str(tmp_path / "v.bin"), 365, 7, nvar=8)
+    assert np.array_equal(np.asarray(sio.open_series(str(tmp_path / "v.bin"))), vali)
+    w = sio.create_series(str(tmp_path / "o.bin"), 3, 8, 5)
+    w[...] = 1.5
+    w.flush()
+    assert np.array_equal(np.asarray(sio.open_series(str(tmp_path / "o.bin"))), np.full((3, 8, 5), 1.5))
+    (tmp_path / "bad.bin").write_bytes(b"x" * 100)
+    with pytest.raises(ValueError):
+        sio.open_series(str(tmp_path / "bad.bin"))
