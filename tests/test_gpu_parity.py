@@ -281,6 +281,34 @@ def test_period_means_in_kernel():
         fs.free(); means.free()
 
 
+def test_synthetic_ten_years_window_forcing():
+    """the bench's C3 protocol at oracle size: 10 years as 10 x 365 days over the 73-day periodic window (one row per
+    5 calendar days), slater, n_ksub=3; the 1e-10 bar still holds for the last simulated year"""
+    from semic_b200 import engine
+    nx, nwin = 768, 73
+    fs = engine.Series(nx, 9, nwin).synth_forcing(20260101, point0=4242, dayofs=0, daystride=5)
+    forc = fs.download()
+    fs.free()
+    r = np.random.default_rng(11)
+    mask = r.choice(np.array([2, 1, 0], dtype=np.int32), size=nx, p=[0.97, 0.02, 0.01]).astype(np.int32)   # Antarctica-like
+    g = _gpu()
+    S0, m0 = util.init_slab(nx, mask)
+    par = dict(util.PAR_SLATER, n_ksub=3)
+    ndays = 3650
+    fin_l, out_l, _, _ = g.run_gpu(S0, m0, par, (), forc, ndays, out_days=365, branch=False)          # k_run_lean
+    fin_b, out_b, br_b, _ = g.run_gpu(S0, m0, par, (), forc, ndays, out_days=ndays, branch=True)      # bitmap over all days
+    fin_o, out_o, br_o = g.run_oracle(S0, m0, par, (), forc, ndays, out_days=ndays)
+    taint = util.tainted(br_b, br_o)[ndays - 365:]
+    pts = taint.any(axis=0)
+    oe = util.out_errors(out_l, out_o[ndays - 365:], exclude=taint)
+    se = util.state_errors(fin_l, fin_o, exclude_points=pts)
+    print("\n[10 years] last-year max rel err %.3e, final state %.3e, tainted points %d of %d"
+          % (max(oe.values()), max(se.values()), int(pts.sum()), nx))
+    assert max(oe.values()) <= TOL and max(se.values()) <= TOL
+    assert pts.sum() <= 0.05 * nx
+    assert np.array_equal(out_l, out_b[ndays - 365:])
+
+
 def test_synthetic_statistics():
     """the device generator stays inside the ranges of SURVEY 8(d) / the shipped forcing"""
     from semic_b200 import engine
