@@ -1,5 +1,5 @@
-"""Prints a parity + flip report (GPU vs oracle) for a few configurations.  Run on the GPU box:
-   python tools/parity_report.py [transect|synthetic] [k] [scheme] [strict]"""
+"""Test infrastructure (uses the CPU oracle): prints a parity + flip report (GPU vs oracle) for a few configurations.  Run on the GPU box:
+   python tests/parity_report.py [transect|synthetic] [k] [scheme] [strict]"""
 import sys, os
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np
