@@ -1192,19 +1192,40 @@ __global__ void __launch_bounds__(WPC * 32, 1) k_run_lean(const __grid_constant_
 // last loop; crmsd^2 = (sum(e^2) - sum(e)^2/n)/n / var(validation).  Per-particle sums over the CTA's
 // 32 points go to partial[particle][tile] (fixed-order second stage: bitwise reproducible).
 constexpr int kEnsParticles = 8;
+constexpr int kEnsStages = 2;
+constexpr int kEnsRows = kForcingRows + 4;                          // forcing + validation stt | swnet smb melt
+struct EnsSmem {
+    static constexpr uint32_t stage_bytes = kEnsRows * kTile * (uint32_t)sizeof(double);          // 3328 B
+    static constexpr size_t ring_bytes = (size_t)stage_bytes * kEnsStages * kEnsParticles;
+    static constexpr size_t bar_bytes = (size_t)kEnsParticles * kEnsStages * sizeof(uint64_t);
+    static constexpr size_t par_bytes = (size_t)kEnsParticles * sizeof(DevPar);
+    static constexpr size_t bytes = ring_bytes + bar_bytes + par_bytes + kExpTab * sizeof(double);   // 3 CTAs per SM
+};
 
 // SCHEME / NK: albedo scheme and n_ksub as compile-time constants when every particle shares them (optimize/tools.py:31,35
 // writes n_ksub = 3 and alb_scheme = "none" into every particle's namelist); SCHEME_RUNTIME / 0 otherwise.
+// Like k_run_lean every warp feeds itself: a private 2-stage ring, one bulk copy of the day's 9 forcing rows plus two of
+// the validation rows it is scored against (stt; swnet, smb, melt are adjacent), so no load latency sits in the day loop
+// (the eight warps of a CTA fetch the same tile-days: L2 hits).
 template <int SCHEME, int NK>
-__global__ void __launch_bounds__(32 * kEnsParticles, 3) k_ensemble(const EnsArgs a, const int ngroups)
+__global__ void __launch_bounds__(32 * kEnsParticles, 3) k_ensemble(const __grid_constant__ EnsArgs a, const int ngroups)
 {
-    __shared__ DevPar s_par[kEnsParticles];
-    __shared__ double tab[kExpTab];
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    constexpr uint32_t SB = EnsSmem::stage_bytes;
+    constexpr uint32_t FB = kForcingRows * kTile * (uint32_t)sizeof(double);
+    constexpr uint32_t RB = kTile * (uint32_t)sizeof(double);                                     // one row
+    const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
+    const int lane = threadIdx.x & 31;
+    const uint32_t smem_u = smem_u32(smem_raw);
+    const uint32_t ring_u = smem_u + (uint32_t)(warp * kEnsStages) * SB;
+    const uint32_t bar_u = smem_u + (uint32_t)EnsSmem::ring_bytes + (uint32_t)(warp * kEnsStages) * 8u;
+    const double *ring = reinterpret_cast<const double *>(smem_raw + (size_t)(warp * kEnsStages) * SB) + lane;
+    DevPar *s_par = reinterpret_cast<DevPar *>(smem_raw + EnsSmem::ring_bytes + EnsSmem::bar_bytes);
+    double *tab = reinterpret_cast<double *>(smem_raw + EnsSmem::ring_bytes + EnsSmem::bar_bytes + EnsSmem::par_bytes);
+
     for (int j = threadIdx.x; j < kExpTab; j += 32 * kEnsParticles) tab[j] = g_exp2_tab[j];
     const int tile = blockIdx.x / ngroups;
     const int group = blockIdx.x % ngroups;
-    const int lane = threadIdx.x & 31;
-    const int warp = threadIdx.x >> 5;
     const int p = group * kEnsParticles + warp;
     const bool pvalid = p < a.npar;
     {   // stage the CTA's parameter sets
@@ -1213,55 +1234,82 @@ __global__ void __launch_bounds__(32 * kEnsParticles, 3) k_ensemble(const EnsArg
         double *dst = reinterpret_cast<double *>(&s_par[warp]);
         for (int w = lane; w < nwords; w += 32) dst[w] = src[w];
     }
+    if (lane == 0) {
+        for (int st = 0; st < kEnsStages; ++st) mbar_init(bar_u + 8u * st, 1);
+        mbar_fence_init();
+    }
     __syncthreads();
     const DevPar &P = s_par[warp];
     const long long i = (long long)tile * 32 + lane;
     const bool valid = pvalid && i < a.nx;
-    const long long ii = (i < a.nx) ? i : 0;
     semic_bnd B;
     B.t2m = B.tsurf = B.hsnow = B.alb = B.melt = B.refr = B.smb = B.acc = B.lhf = B.shf = B.subl = B.amp = 0;
 
-    Pt s;
-    const double *S = a.slab0 + ii;
     const long long ld = a.ld;
     const long long ntl = ld / kTile;
-    s.mask = a.mask[ii];
-    s.tsurf = S[SEMIC_F_TSURF * ld];
-    s.hsnow = S[SEMIC_F_HSNOW * ld];
-    s.hice = S[SEMIC_F_HICE * ld];
-    s.alb = S[SEMIC_F_ALB * ld];
-    s.alb_snow = S[SEMIC_F_ALB_SNOW * ld];
-    s.qmr_res = S[SEMIC_F_QMR_RES * ld];
-    s.melt = s.melted_snow = s.melted_ice = s.refr = s.smb = s.acc = 0.0;
-    s.lhf = s.shf = s.lwu = s.subl = s.evap = s.smb_snow = s.smb_ice = s.runoff = s.qmr = s.amp = s.t2m = 0.0;
+    const double *ftile = a.forcing + (long long)tile * (kForcingRows * kTile);
+    const double *vtile = a.vali + (long long)tile * (SEMIC_NOUT * kTile);
+    const long long f_day = ntl * (kForcingRows * kTile), v_day = ntl * (SEMIC_NOUT * kTile);
+    const int total = a.nloop * a.ntime;                          // days of this trajectory
+    int n_issue = 0, d_issue = 0;                                 // forcing row and count of the next day to fetch
+    auto issue = [&](const uint32_t st) {
+        if (elect_one()) {
+            const uint32_t dst = ring_u + st * SB, bar = bar_u + 8u * st;
+            const double *v = vtile + (long long)n_issue * v_day;
+            mbar_expect_tx(bar, FB + 4u * RB);
+            tma_load_1d(dst, ftile + (long long)n_issue * f_day, FB, bar);
+            tma_load_1d(dst + FB, v + SEMIC_O_STT * kTile, RB, bar);                              // row 9: stt
+            tma_load_1d(dst + FB + RB, v + SEMIC_O_SWNET * kTile, 3u * RB, bar);                  // rows 10-12: swnet smb melt
+        }
+        ++d_issue;
+        if (++n_issue == a.ntime) n_issue = 0;
+    };
+    for (uint32_t st = 0; st < (uint32_t)kEnsStages && d_issue < total; ++st) issue(st);
+
+    Pt s;
+    {
+        const double *S = a.slab0 + i;                            // the slab has ld >= ntiles*32 columns
+        s.mask = a.mask[i];
+        s.tsurf = S[SEMIC_F_TSURF * ld];
+        s.hsnow = S[SEMIC_F_HSNOW * ld];
+        s.hice = S[SEMIC_F_HICE * ld];
+        s.alb = S[SEMIC_F_ALB * ld];
+        s.alb_snow = S[SEMIC_F_ALB_SNOW * ld];
+        s.qmr_res = S[SEMIC_F_QMR_RES * ld];
+        s.melt = s.melted_snow = s.melted_ice = s.refr = s.smb = s.acc = 0.0;
+        s.lhf = s.shf = s.lwu = s.subl = s.evap = s.smb_snow = s.smb_ice = s.runoff = s.qmr = s.amp = s.t2m = 0.0;
+    }
 
     double d0[4] = {0, 0, 0, 0}, se[4] = {0, 0, 0, 0}, see[4] = {0, 0, 0, 0};
-    for (int k = 0; k < a.nloop; ++k) {
-        const bool lastloop = (k == a.nloop - 1);
-        for (int n = 0; n < a.ntime; ++n) {
-            const double *row = a.forcing + ((long long)n * ntl + tile) * (kForcingRows * kTile) + lane;
-            double swd;
-            point_day<SCHEME, false, false, (NK > 0 ? NK : 2), NK>(s, row, kTile, P, B, P.n_ksub, 1, swd, tab);
-            if (lastloop) {                                              // run_particles.f90:148-157
-                const double *v = a.vali + ((long long)n * ntl + tile) * (SEMIC_NOUT * kTile) + lane;
-                double d[4];
-                d[0] = s.tsurf - v[SEMIC_O_STT * kTile];
-                d[1] = s.melt - v[SEMIC_O_MELT * kTile];
-                d[2] = s.smb - v[SEMIC_O_SMB * kTile];
-                d[3] = swd * (1.0 - s.alb) - v[SEMIC_O_SWNET * kTile];
+    uint32_t stage = 0, phase = 0;
+    const int first_scored = total - a.ntime;                     // the last loop is scored (run_particles.f90:148)
+    for (int day = 0; day < total; ++day) {
+        mbar_wait(bar_u + 8u * stage, phase);
+        const double *row = ring + (size_t)stage * (SB / sizeof(double));
+        double swd;
+        point_day<SCHEME, false, false, (NK > 0 ? NK : 2), NK>(s, row, kTile, P, B, P.n_ksub, 1, swd, tab);
+        if (day >= first_scored) {                                               // run_particles.f90:148-157
+            double d[4];
+            d[0] = s.tsurf - row[(kForcingRows + 0) * kTile];                    // stt
+            d[1] = s.melt - row[(kForcingRows + 3) * kTile];                     // melt
+            d[2] = s.smb - row[(kForcingRows + 2) * kTile];                      // smb
+            d[3] = swd * (1.0 - s.alb) - row[(kForcingRows + 1) * kTile];        // swnet
 #pragma unroll
-                for (int q = 0; q < 4; ++q) {
-                    if (n == 0) d0[q] = d[q];
-                    const double e = d[q] - d0[q];
-                    se[q] += e;
-                    see[q] = fma(e, e, see[q]);
-                }
+            for (int q = 0; q < 4; ++q) {
+                if (day == first_scored) d0[q] = d[q];
+                const double e = d[q] - d0[q];
+                se[q] += e;
+                see[q] = fma(e, e, see[q]);
             }
         }
+        __syncwarp();
+        if (d_issue < total) issue(stage);
+        if (++stage == (uint32_t)kEnsStages) { stage = 0; phase ^= 1u; }
     }
     // sum over the 4 variables of crmsd^2 (run_particles.f90:172-174)
     double c = 0.0;
     const double n = (double)a.ntime;
+    const long long ii = (i < a.nx) ? i : 0;
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
         const double var_d = dmax1(0.0, (see[q] - se[q] * se[q] / n) / n);

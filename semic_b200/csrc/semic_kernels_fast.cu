@@ -94,15 +94,17 @@ cudaError_t launch_ensemble_fast(const EnsArgs &a, double *sumsq_dev, cudaStream
     const long long nblocks = (long long)a.ntiles * ngroups;
     if (nblocks > 0x7fffffffLL) return cudaErrorInvalidValue;
     const dim3 grid((unsigned)nblocks), block(32 * fast_mode::kEnsParticles);
+    const size_t smem = fast_mode::EnsSmem::bytes;
     const bool k3 = a.uni_ksub == 3;
-    if (a.uni_scheme == SCHEME_NONE) {
-        if (k3) fast_mode::k_ensemble<SCHEME_NONE, 3><<<grid, block, 0, st>>>(a, ngroups);
-        else    fast_mode::k_ensemble<SCHEME_NONE, 0><<<grid, block, 0, st>>>(a, ngroups);
-    } else {
-        if (k3) fast_mode::k_ensemble<SCHEME_RUNTIME, 3><<<grid, block, 0, st>>>(a, ngroups);
-        else    fast_mode::k_ensemble<SCHEME_RUNTIME, 0><<<grid, block, 0, st>>>(a, ngroups);
-    }
-    cudaError_t e = cudaGetLastError();
+    auto go = [&](auto kern) -> cudaError_t {
+        cudaError_t err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (err != cudaSuccess) return err;
+        kern<<<grid, block, smem, st>>>(a, ngroups);
+        return cudaGetLastError();
+    };
+    cudaError_t e;
+    if (a.uni_scheme == SCHEME_NONE) e = k3 ? go(fast_mode::k_ensemble<SCHEME_NONE, 3>) : go(fast_mode::k_ensemble<SCHEME_NONE, 0>);
+    else                             e = k3 ? go(fast_mode::k_ensemble<SCHEME_RUNTIME, 3>) : go(fast_mode::k_ensemble<SCHEME_RUNTIME, 0>);
     if (e != cudaSuccess) return e;
     fast_mode::k_ens_reduce<<<(a.npar + 127) / 128, 128, 0, st>>>(a.partial, a.ntiles, a.npar, sumsq_dev);
     return cudaGetLastError();
