@@ -3,6 +3,13 @@ written from surface_physics.f90 directly (not from the C oracle).  Slow; used o
 the oracle (tests/test_oracle.py).  math.exp/acos/sqrt/pow/tanh are glibc's, like gfortran's."""
 import math
 
+import numpy as _np
+
+
+def _ieee_div(a, b):
+    with _np.errstate(all="ignore"):
+        return float(_np.float64(a) / _np.float64(b))
+
 T0, SIGM, EPS, CLS, CLM, CLV, CAP, RHOW, HSMAX = 273.15, 5.67e-8, 0.62197, 2.83e6, 3.30e5, 2.5e6, 1000.0, 1000.0, 5.0
 EPSIL = 2.220446049250313e-16
 PI = 3.141592653589793238462643
@@ -47,9 +54,10 @@ def step_point(s, par, bnd, mask):
     amp = s["amp"]
     tmean = s["tsurf"] - T0 + s["qmr"] / par["ceff"] * par["tstic"]
     tmp1 = tmp2 = 0.0
-    if abs(tmean / amp) < 1.0:
-        tmp1 = math.acos(tmean / amp)
-        tmp2 = math.sqrt(1.0 - tmean * tmean / (amp * amp))
+    r = _ieee_div(tmean, amp)                                   # amp = 0: inf or NaN as in Fortran, not an exception
+    if abs(r) < 1.0:
+        tmp1 = math.acos(r)
+        tmp2 = math.sqrt(1.0 - _ieee_div(tmean * tmean, amp * amp))
     if tmean + amp < 0.0:
         below, above = tmean, 0.0
     else:

@@ -201,6 +201,40 @@ def test_lean_kernel_with_external_tsurf_and_alb(names, k):
     assert max(oe.values()) <= TOL and max(se.values()) <= TOL
 
 
+@pytest.mark.parametrize("case", ["odd_masks", "amp_zero", "hcrit_zero", "unused_minus_999"])
+def test_lean_kernel_corner_cases(case):
+    """Q7 (mask values other than 0/1/2), amp = 0, hcrit = 0 and -999 "unused" parameters put to use, on both kernels"""
+    g = _gpu()
+    nx, nwin, ndays = 333, 40, 160
+    forc = util.random_forcing(nx, nwin, seed=41)
+    r = np.random.default_rng(9)
+    mask = r.choice(np.array([2, 1, 0], dtype=np.int32), size=nx, p=[0.8, 0.15, 0.05]).astype(np.int32)
+    par = dict(util.PAR_SLATER, n_ksub=3)
+    if case == "odd_masks":
+        mask = r.choice(np.array([2, 1, 0, 3, -1, 7], dtype=np.int32), size=nx).astype(np.int32)
+    elif case == "amp_zero":
+        par["amp"] = 0.0
+    elif case == "hcrit_zero":
+        par["hcrit"] = 0.0
+    else:
+        par = dict(util.PAR_EXAMPLE, alb_scheme="slater")            # alb_smin = tmin = -999
+    S0, m0 = util.init_slab(nx, mask)
+    fin_l, out_l, _, _ = g.run_gpu(S0, m0, par, (), forc, ndays, out_days=ndays, branch=False)
+    fin_b, out_b, br_b, _ = g.run_gpu(S0, m0, par, (), forc, ndays, out_days=ndays, branch=True)
+    fin_o, out_o, br_o = g.run_oracle(S0, m0, par, (), forc, ndays, out_days=ndays)
+    assert np.array_equal(out_l, out_b, equal_nan=True) and np.array_equal(fin_l[:23], fin_b[:23], equal_nan=True)
+    assert np.isfinite(out_l).all() and np.isfinite(out_o).all()
+    taint = util.tainted(br_b, br_o)
+    oe = util.out_errors(out_l, out_o, exclude=taint)
+    se = util.state_errors(fin_l, fin_o, exclude_points=taint.any(axis=0))
+    print("\n[corner %s] daily %.2e state %.2e tainted points %d" % (case, max(oe.values()), max(se.values()),
+                                                                     int(taint.any(axis=0).sum())))
+    assert max(oe.values()) <= TOL and max(se.values()) <= TOL
+    if case == "odd_masks":
+        odd = ~np.isin(mask, (0, 1, 2))
+        assert (out_l[:, 1, odd] == S0[util.ob.FIDX["alb"], odd]).all()     # alb is never assigned (:350-358)
+
+
 def test_lean_kernel_output_ring_and_chunks():
     """daily output into a ring shorter than the run keeps the last days; a run cut into launches continues bit for bit"""
     from semic_b200 import engine

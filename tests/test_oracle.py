@@ -117,6 +117,33 @@ def test_oracle_equals_independent_python_restatement(scheme, bnd_names):
     assert np.array_equal(Sa[:23], Sb[:23])
 
 
+@pytest.mark.parametrize("case", ["odd_masks", "amp_zero", "hcrit_zero", "unused_minus_999"])
+def test_oracle_equals_python_restatement_on_the_corner_cases(case):
+    """Q7 (mask values other than 0/1/2 leave alb unchanged), amp = 0 (diurnal_cycle divides by it, :450), hcrit = 0
+    (the f_alb exponent divides by epsilon, :338) and the namelists' -999 "unused" values (Q15) put to use by slater"""
+    forc, vali = util.load_fixture("transect")
+    mask = np.array([1, 0, 1, 2, 2, 2, 2], dtype=np.int32)
+    pd = dict(util.PAR_SLATER, n_ksub=3)
+    if case == "odd_masks":
+        mask = np.array([3, 0, -1, 2, 7, 1, 2], dtype=np.int32)
+    elif case == "amp_zero":
+        pd["amp"] = 0.0
+    elif case == "hcrit_zero":
+        pd["hcrit"] = 0.0
+    else:
+        pd = dict(util.PAR_EXAMPLE, alb_scheme="slater")             # alb_smin = tmin = -999 (example.namelist:17,20) in use
+    S0, m0 = util.init_slab(7, mask)
+    Sa = S0.copy()
+    out_a, _ = ob.run(Sa, m0.copy(), ob.make_par(pd), ob.make_bnd(()), forc, 200, out_days=200)
+    Sb = S0.copy()
+    out_b = pyref.run(Sb, m0, ob.FIELDS, pd, {}, forc, 200)
+    assert np.array_equal(out_a, out_b, equal_nan=True)
+    assert np.array_equal(Sa[:23], Sb[:23], equal_nan=True)
+    if case == "odd_masks":
+        for i in (0, 2, 4):                                          # alb is never assigned for these points (:350-358)
+            assert (out_a[:, 1, i] == S0[ob.FIDX["alb"], i]).all()
+
+
 def test_invariants_on_random_forcing():
     nx, nd = 500, 400
     forc = util.random_forcing(nx, nd, seed=2)
