@@ -266,11 +266,20 @@ __global__ void k_tiled_to_soa(const double *tiled, int ld, int nvar, int day0, 
     }
 }
 
-// one variable of one day of a tiled series -> a contiguous row
-__global__ void k_tiled_var_to_row(const double *tiled, int ld, int nvar, int day, int var, int np, double *dst)
+// the 8 forcing variables sf..qq of one day of a tiled forcing series -> the state slab's forcing fields (t2m, the 9th,
+// is written by the step kernel itself: the reference mutates it, surface_physics.f90:209-211)
+__constant__ int c_forcing_dst_field[kForcingRows] = {SEMIC_F_SF, SEMIC_F_RF, SEMIC_F_SWD, SEMIC_F_LWD, SEMIC_F_WIND,
+                                                      SEMIC_F_SP, SEMIC_F_RHOA, SEMIC_F_QQ, -1};
+__global__ void k_tiled_day_to_slab(const double *tiled, int ld_series, int day, int np, double *slab, long long ld_slab)
 {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < np) dst[i] = tiled[(((long long)day * (ld / kTile) + i / kTile) * nvar + var) * kTile + (i % kTile)];
+    if (i >= np) return;
+    const double *src = tiled + ((long long)day * (ld_series / kTile) + i / kTile) * (kForcingRows * kTile) + (i % kTile);
+#pragma unroll
+    for (int v = 0; v < kForcingRows; ++v) {
+        const int f = c_forcing_dst_field[v];
+        if (f >= 0) slab[(long long)f * ld_slab + i] = src[v * kTile];
+    }
 }
 
 // field_average, surface_physics.f90:601-629, over the 19 averaged fields (:574-593)
@@ -807,13 +816,7 @@ static void fill_run_args(RunArgs &a, semic_state *now, const semic_par *par, co
 static int copy_last_forcing(semic_state *now, const double *forcing, int f_nwin, int day0, int ndays)
 {
     const int fd = (((day0 + ndays - 1) % f_nwin) + f_nwin) % f_nwin;
-    const int dst_field[kForcingRows] = {SEMIC_F_SF, SEMIC_F_RF, SEMIC_F_SWD, SEMIC_F_LWD, SEMIC_F_WIND, SEMIC_F_SP,
-                                         SEMIC_F_RHOA, SEMIC_F_QQ, -1};      // t2m is written by the kernel (mutated)
-    for (int v = 0; v < kForcingRows; ++v) {
-        if (dst_field[v] < 0) continue;
-        k_tiled_var_to_row<<<(now->npts + 255) / 256, 256, 0, now->stream>>>(forcing, now->ld, SEMIC_NFORCING, fd, v, now->npts,
-                                                                            now->d_slab + (size_t)dst_field[v] * now->ld);
-    }
+    k_tiled_day_to_slab<<<(now->npts + 255) / 256, 256, 0, now->stream>>>(forcing, now->ld, fd, now->npts, now->d_slab, now->ld);
     CU(cudaGetLastError());
     return SEMIC_OK;
 }
@@ -956,8 +959,6 @@ extern "C" int semic_run_host(semic_state *now, const semic_par *par, const semi
 
     const int nchunks = (ndays + chunk_days - 1) / chunk_days;
     const int out_first = ndays - out_days;
-    const int dst_field[kForcingRows] = {SEMIC_F_SF, SEMIC_F_RF, SEMIC_F_SWD, SEMIC_F_LWD, SEMIC_F_WIND, SEMIC_F_SP,
-                                         SEMIC_F_RHOA, SEMIC_F_QQ, -1};      // t2m is written by the kernel (mutated)
     CUX(cudaEventRecord(t0, now->stream));
     CUX(cudaStreamWaitEvent(s_in, t0, 0));
     long long unit = 0;
@@ -1004,11 +1005,7 @@ extern "C" int semic_run_host(semic_state *now, const semic_par *par, const semi
                 CUX(cudaGetLastError());
             }
             if (c == nchunks - 1) {           // the state's forcing fields hold the last day's forcing, as after the reference's loop
-                for (int v = 0; v < kForcingRows; ++v) {
-                    if (dst_field[v] < 0) continue;
-                    k_tiled_var_to_row<<<(np + 255) / 256, 256, 0, now->stream>>>(d_ft[b], sld, SEMIC_NFORCING, nd - 1, v, np,
-                                                                                now->d_slab + (size_t)dst_field[v] * ld + p0);
-                }
+                k_tiled_day_to_slab<<<(np + 255) / 256, 256, 0, now->stream>>>(d_ft[b], sld, nd - 1, np, now->d_slab + p0, ld);
                 CUX(cudaGetLastError());
             }
             CUX(cudaEventRecord(ev_k[b], now->stream));
