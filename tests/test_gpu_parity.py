@@ -403,7 +403,7 @@ def test_dropin_daily_step_module_api(tmp_path):
     forc, vali = util.load_fixture("transect")
     nx, ntime = 7, 60
     nml = tmp_path / "test.nml"
-    nml.write_text(open(util.GOLDEN + "/test_slater.nml").read())
+    util.write_slater_namelist(str(nml))
     par = sp.surface_physics.Surface_Param_Class()
     sp.surface_physics.surface_physics_par_load(par, str(nml))
     par.nx = nx
@@ -805,8 +805,7 @@ def test_run_example_program(tmp_path):
     (tmp_path / "data").mkdir()
     np.savetxt(tmp_path / "data" / "transect_input.txt", forc.reshape(365, -1))
     np.savetxt(tmp_path / "data" / "transect_output.txt", vali.reshape(365, -1))
-    nml = open(util.GOLDEN + "/example.nml").read().replace("nloop = 100", "nloop = 3")
-    (tmp_path / "example.namelist").write_text(nml)
+    util.write_example_namelist(str(tmp_path / "example.namelist"), nloop=3)
     out, now, par, bnd = driver.run_example(str(tmp_path / "example.namelist"))
     # oracle twin of example.f90:74-127
     mask = np.array([1, 1, 1, 2, 2, 2, 2], dtype=np.int32)

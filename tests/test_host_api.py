@@ -56,11 +56,11 @@ def test_struct_layout_matches_header():
     assert _capi.SemicPar.ceff.offset == 256 * 32 + 8
 
 
-def test_par_load_example_namelist():
+def test_par_load_example_namelist(tmp_path):
     par = sp.Surface_Param_Class()
     par.afac = 123.0                      # not in the file: keeps the incoming value (surface_physics.f90:752-775)
     par.tmid = -4.0
-    sp.surface_physics_par_load(par, os.path.join(util.GOLDEN, "example.nml"))
+    sp.surface_physics_par_load(par, util.write_example_namelist(str(tmp_path / "example.namelist")))
     exp = util.PAR_EXAMPLE
     for k in ("tstic", "ceff", "csh", "clh", "alb_smax", "alb_smin", "albi", "albl", "tmin", "tmax", "hcrit", "rcrit",
               "amp", "tau_a", "tau_f", "w_crit", "mcrit"):
@@ -135,9 +135,9 @@ def test_boundary_define_names():
     assert not any(getattr(bnd, n) for n in _capi.BND_NAMES)
 
 
-def test_print_param_and_boundary_opt(capfd):
+def test_print_param_and_boundary_opt(capfd, tmp_path):
     par = sp.Surface_Param_Class()
-    sp.surface_physics_par_load(par, os.path.join(util.GOLDEN, "test_slater.nml"))
+    sp.surface_physics_par_load(par, util.write_slater_namelist(str(tmp_path / "test.nml")))
     par.nx = 7
     par.boundary = ["tsurf"]
     sp.print_param(par)
@@ -170,8 +170,8 @@ def test_compute_entries_fail_loudly_without_a_gpu():
         sp.longwave_upward(np.array([273.15]), sp.sigm)
 
 
-def test_driver_namelist_and_shards():
-    d = driver.read_driver_namelist(os.path.join(util.GOLDEN, "example.nml"))
+def test_driver_namelist_and_shards(tmp_path):
+    d = driver.read_driver_namelist(util.write_example_namelist(str(tmp_path / "example.namelist")))
     assert (d["nloop"], d["ntime"], d["nx"]) == (100, 365, 7)
     assert list(d["loi_mask"][:7]) == [1, 1, 1, 2, 2, 2, 2] and d["output"] == "example.out"
     for n, w in ((16777216, 8), (100000, 8), (7, 3), (5, 8), (0, 2)):
@@ -217,8 +217,7 @@ def _example_dir(tmp_path, nloop=2):
     (tmp_path / "data").mkdir()
     np.savetxt(tmp_path / "data" / "transect_input.txt", forc.reshape(365, -1))
     np.savetxt(tmp_path / "data" / "transect_output.txt", vali.reshape(365, -1))
-    nml = open(util.GOLDEN + "/example.nml").read().replace("nloop = 100", "nloop = %d" % nloop)
-    (tmp_path / "example.namelist").write_text(nml)
+    util.write_example_namelist(str(tmp_path / "example.namelist"), nloop=nloop)
     return tmp_path
 
 
