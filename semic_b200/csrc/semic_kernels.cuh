@@ -996,19 +996,21 @@ DEVI bool elect_one()
 // AVG: instead of every day's 8 fields, their means over consecutive periods of a.avg_days days are written (the
 // surface_physics_average protocol, surface_physics.f90:565-629: zero at 'init', add at every 'step', divide by the
 // number of steps at 'end'), accumulated in registers: the daily 64 B/point of output traffic become 64/avg_days.
-// EXT: bnd%tsurf and/or bnd%alb with an external series (BASELINE configs[3]; example.f90:103-104): the day's rows
+// EXT = 1: bnd%tsurf and/or bnd%alb with an external series (BASELINE configs[3]; example.f90:103-104): the day's rows
 // stt / alb of the validation-layout series ride in the same stage as the forcing (one more bulk copy of 256 or 512 B).
-template <int WPC, bool EXT>
+// EXT = 2: any set of boundary flags (the GENERIC physics: all 23 fields carried, flagged fields keep their state value or
+// come from the external rows stt alb smb melt acc, example.f90:103-107) on the same shell; 16 warps x 128 registers.
+template <int WPC, int EXT>
 struct LeanSmem {
-    static constexpr int ROWS = kForcingRows + (EXT ? 2 : 0);
+    static constexpr int ROWS = kForcingRows + (EXT == 2 ? 6 : (EXT == 1 ? 2 : 0));
     static constexpr int STAGES = kStages;
-    static constexpr size_t stage_bytes = (size_t)ROWS * kTile * sizeof(double);           // 2304 B (2816 B with external rows)
+    static constexpr size_t stage_bytes = (size_t)ROWS * kTile * sizeof(double);           // 2304 B (2816 / 3840 B with external rows)
     static constexpr size_t ring_bytes = stage_bytes * STAGES * WPC;
     static constexpr size_t bar_bytes = (size_t)WPC * STAGES * sizeof(uint64_t);
     static constexpr size_t bytes = ring_bytes + bar_bytes + kExpTab * sizeof(double);      // rings, barriers, exp table
 };
 
-template <int SCHEME, int WPC, int UNR, int NK, bool AVG = false, bool EXT = false>
+template <int SCHEME, int WPC, int UNR, int NK, bool AVG = false, int EXT = 0>
 __global__ void __launch_bounds__(WPC * 32, 1) k_run_lean(const __grid_constant__ RunArgs a)
 {
     using SM = LeanSmem<WPC, EXT>;
@@ -1045,18 +1047,24 @@ __global__ void __launch_bounds__(WPC * 32, 1) k_run_lean(const __grid_constant_
     asm volatile("" : "+r"(ostart));                             // keep it in a register instead of re-deriving it daily
     uint32_t stage = 0, phase = 0;
     // external rows: stt (row 0) and alb (row 1) of the validation layout are adjacent: one copy covers what is flagged
-    const bool x_ts = EXT && a.B.tsurf != 0, x_alb = EXT && a.B.alb != 0;
-    const int x_row0 = x_ts ? SEMIC_O_STT : SEMIC_O_ALB;
-    const uint32_t x_bytes = EXT ? (uint32_t)((x_ts ? 1 : 0) + (x_alb ? 1 : 0)) * kTile * (uint32_t)sizeof(double) : 0u;
-    const uint32_t x_dst = FB + (uint32_t)x_row0 * kTile * (uint32_t)sizeof(double);       // stage rows 9 (stt), 10 (alb)
+    // (EXT = 2: also smb, melt, acc; the copy spans first .. last flagged row of stt alb swnet smb melt acc)
+    const bool x_on = EXT != 0 && a.vali != nullptr;
+    const bool x_ts = x_on && a.B.tsurf != 0, x_alb = x_on && a.B.alb != 0;
+    const bool x_smb = EXT == 2 && x_on && a.B.smb != 0, x_melt = EXT == 2 && x_on && a.B.melt != 0;
+    const bool x_acc = EXT == 2 && x_on && a.B.acc != 0;
+    const int x_row0 = x_ts ? SEMIC_O_STT : x_alb ? SEMIC_O_ALB : x_smb ? SEMIC_O_SMB : x_melt ? SEMIC_O_MELT : SEMIC_O_ACC;
+    const int x_row1 = x_acc ? SEMIC_O_ACC : x_melt ? SEMIC_O_MELT : x_smb ? SEMIC_O_SMB : x_alb ? SEMIC_O_ALB : SEMIC_O_STT;
+    const bool x_any = x_ts || x_alb || x_smb || x_melt || x_acc;
+    const uint32_t x_bytes = x_any ? (uint32_t)(x_row1 - x_row0 + 1) * kTile * (uint32_t)sizeof(double) : 0u;
+    const uint32_t x_dst = FB + (uint32_t)x_row0 * kTile * (uint32_t)sizeof(double);       // stage rows 9 (stt) .. 14 (acc)
     const long long v_day = ntl * OBLK;                          // doubles per day of the external series
 
     for (long long tile = (long long)blockIdx.x * WPC + warp; tile < ntiles; tile += nwarps) {
         const double *ftile = a.forcing + tile * FBLK;
         int fd = a.f_day0 % a.f_nwin;                            // next forcing day to fetch and its address
         const double *fsrc = ftile + (long long)fd * f_day;
-        const double *vtile = EXT ? a.vali + tile * OBLK + (long long)x_row0 * kTile : nullptr;
-        const double *vsrc = EXT ? vtile + (long long)fd * v_day : nullptr;
+        const double *vtile = x_any ? a.vali + tile * OBLK + (long long)x_row0 * kTile : nullptr;
+        const double *vsrc = x_any ? vtile + (long long)fd * v_day : nullptr;
         int d_issue = 0;
         {
             uint32_t s = stage;
@@ -1065,11 +1073,11 @@ __global__ void __launch_bounds__(WPC * 32, 1) k_run_lean(const __grid_constant_
                 if (elect_one()) {
                     mbar_expect_tx(bar_u + 8u * s, FB + x_bytes);
                     tma_load_1d(ring_u + s * SB, fsrc, FB, bar_u + 8u * s);
-                    if (EXT) tma_load_1d(ring_u + s * SB + x_dst, vsrc, x_bytes, bar_u + 8u * s);
+                    if (EXT && x_any) tma_load_1d(ring_u + s * SB + x_dst, vsrc, x_bytes, bar_u + 8u * s);
                 }
                 fsrc += f_day;
-                if (EXT) vsrc += v_day;
-                if (++fd == a.f_nwin) { fd = 0; fsrc = ftile; if (EXT) vsrc = vtile; }
+                if (EXT && x_any) vsrc += v_day;
+                if (++fd == a.f_nwin) { fd = 0; fsrc = ftile; if (EXT && x_any) vsrc = vtile; }
                 if (++s == NST) s = 0;
             }
         }
@@ -1087,9 +1095,29 @@ __global__ void __launch_bounds__(WPC * 32, 1) k_run_lean(const __grid_constant_
             s.alb      = S[SEMIC_F_ALB * ld];
             s.alb_snow = S[SEMIC_F_ALB_SNOW * ld];
             s.qmr_res  = S[SEMIC_F_QMR_RES * ld];
-            s.melt = s.melted_snow = s.melted_ice = s.refr = s.smb = s.acc = 0.0;
-            s.lhf = s.shf = s.lwu = s.subl = s.evap = s.smb_snow = s.smb_ice = 0.0;
-            s.runoff = s.qmr = s.amp = s.t2m = 0.0;
+            if (EXT == 2) {                                      // flagged fields keep their state value
+                s.melt = S[SEMIC_F_MELT * ld];
+                s.melted_snow = S[SEMIC_F_MELTED_SNOW * ld];
+                s.melted_ice = S[SEMIC_F_MELTED_ICE * ld];
+                s.refr = S[SEMIC_F_REFR * ld];
+                s.smb = S[SEMIC_F_SMB * ld];
+                s.acc = S[SEMIC_F_ACC * ld];
+                s.lhf = S[SEMIC_F_LHF * ld];
+                s.shf = S[SEMIC_F_SHF * ld];
+                s.lwu = S[SEMIC_F_LWU * ld];
+                s.subl = S[SEMIC_F_SUBL * ld];
+                s.evap = S[SEMIC_F_EVAP * ld];
+                s.smb_snow = S[SEMIC_F_SMB_SNOW * ld];
+                s.smb_ice = S[SEMIC_F_SMB_ICE * ld];
+                s.runoff = S[SEMIC_F_RUNOFF * ld];
+                s.qmr = S[SEMIC_F_QMR * ld];
+                s.amp = S[SEMIC_F_AMP * ld];
+            } else {
+                s.melt = s.melted_snow = s.melted_ice = s.refr = s.smb = s.acc = 0.0;
+                s.lhf = s.shf = s.lwu = s.subl = s.evap = s.smb_snow = s.smb_ice = 0.0;
+                s.runoff = s.qmr = s.amp = 0.0;
+            }
+            s.t2m = 0.0;
         }
         double *oday = a.out + tile * OBLK + lane;
         int oslot = 0;
@@ -1100,12 +1128,18 @@ __global__ void __launch_bounds__(WPC * 32, 1) k_run_lean(const __grid_constant_
         for (int d = 0; d < ndays; ++d) {
             mbar_wait(bar_u + 8u * stage, phase);
             const double *row = ring + (size_t)stage * (SB / sizeof(double));
-            if (EXT) {                                           // example.f90:103-104
+            if (EXT) {                                           // example.f90:103-107
                 if (x_ts)  s.tsurf = row[(kForcingRows + SEMIC_O_STT) * kTile];
                 if (x_alb) s.alb   = row[(kForcingRows + SEMIC_O_ALB) * kTile];
+                if (EXT == 2) {
+                    if (x_smb)  s.smb  = row[(kForcingRows + SEMIC_O_SMB) * kTile];
+                    if (x_melt) s.melt = row[(kForcingRows + SEMIC_O_MELT) * kTile];
+                    if (x_acc)  s.acc  = row[(kForcingRows + SEMIC_O_ACC) * kTile];
+                }
             }
             double swd;
-            point_day<SCHEME, false, false, UNR, NK, EXT>(s, row, kTile, a.P, a.B, 0, 1, swd, tab);
+            if (EXT == 2) point_day<SCHEME, true, false, UNR, NK, false>(s, row, kTile, a.P, a.B, a.eb_steps, a.do_mb, swd, tab);
+            else          point_day<SCHEME, false, false, UNR, NK, EXT == 1>(s, row, kTile, a.P, a.B, 0, 1, swd, tab);
             if (d >= ostart) {                                   // example.f90:117-122
                 if (!AVG) {
                     oday[SEMIC_O_STT * kTile]   = s.tsurf;
@@ -1170,12 +1204,12 @@ __global__ void __launch_bounds__(WPC * 32, 1) k_run_lean(const __grid_constant_
                 if (elect_one()) {
                     mbar_expect_tx(bar_u + 8u * stage, FB + x_bytes);
                     tma_load_1d(ring_u + stage * SB, fsrc, FB, bar_u + 8u * stage);
-                    if (EXT) tma_load_1d(ring_u + stage * SB + x_dst, vsrc, x_bytes, bar_u + 8u * stage);
+                    if (EXT && x_any) tma_load_1d(ring_u + stage * SB + x_dst, vsrc, x_bytes, bar_u + 8u * stage);
                 }
                 ++d_issue;
                 fsrc += f_day;
-                if (EXT) vsrc += v_day;
-                if (++fd == a.f_nwin) { fd = 0; fsrc = ftile; if (EXT) vsrc = vtile; }
+                if (EXT && x_any) vsrc += v_day;
+                if (++fd == a.f_nwin) { fd = 0; fsrc = ftile; if (EXT && x_any) vsrc = vtile; }
             }
             if (++stage == NST) { stage = 0; phase ^= 1u; }
         }

@@ -69,13 +69,16 @@ cudaError_t launch_run_fast(const RunArgs &a, bool generic, cudaStream_t st, int
         // more rows per stage; every other flag set runs the general kernel (all 23 fields carried)
         const semic_bnd &B = a.B;
         const bool only_ts_alb = (B.tsurf || B.alb) && !(B.shf || B.lhf || B.amp || B.melt || B.refr || B.acc || B.smb);
-        if (only_ts_alb && a.vali != nullptr && lean_ok && !want_avg && !force_general) return fast_mode::launch_lean(a, st, true);
+        if (only_ts_alb && a.vali != nullptr && lean_ok && !want_avg && !force_general) return fast_mode::launch_lean(a, st, 1);
+        // the other flag sets (melt / acc / smb from the external series; shf lhf amp refr frozen at their state values): the
+        // GENERIC physics on the same shell.  k_run<GENERIC> keeps the per-day call, energy_balance / mass_balance alone, the bitmap
+        if (lean_ok && !want_avg && !force_general && a.do_mb && a.eb_steps == a.P.n_ksub) return fast_mode::launch_lean(a, st, 2);
         return fast_mode::launch_scheme<true, 1, 8>(a, st);
     }
     // Plain runs go to k_run_lean; what it does not cover (the bitmap row, the drop-in single day on the slab's own
     // forcing fields, n_ksub < 1) runs k_run.  SEMIC_SHAPE=24x1 forces k_run for A/B timing (tools/ab.py).
     if (want_avg && !lean_ok) return cudaErrorNotSupported;                  // period means: plain runs only
-    if (lean_ok && (want_avg || !force_general)) return fast_mode::launch_lean(a, st, false);
+    if (lean_ok && (want_avg || !force_general)) return fast_mode::launch_lean(a, st, 0);
     return a.P.n_ksub >= 8 ? fast_mode::launch_scheme<false, 1, 24, 4>(a, st) : fast_mode::launch_scheme<false, 1, 24, 2>(a, st);
 }
 

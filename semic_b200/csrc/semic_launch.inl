@@ -42,7 +42,7 @@ static cudaError_t launch_scheme(const RunArgs &a, cudaStream_t st)
 
 #if !SEMIC_STRICT
 // k_run_lean: the plain (no boundary flag) tiled-forcing run with 8 daily rows, n_ksub >= 1
-template <int SCHEME, int WPC, int UNR, int NK, bool AVG, bool EXT>
+template <int SCHEME, int WPC, int UNR, int NK, bool AVG, int EXT>
 static cudaError_t launch_lean_one(const RunArgs &a, cudaStream_t st)
 {
     auto kern = k_run_lean<SCHEME, WPC, UNR, NK, AVG, EXT>;
@@ -61,7 +61,7 @@ static cudaError_t launch_lean_one(const RunArgs &a, cudaStream_t st)
     return cudaGetLastError();
 }
 
-template <int WPC, int UNR, int NK, bool AVG, bool EXT = false>
+template <int WPC, int UNR, int NK, bool AVG, int EXT = 0>
 static cudaError_t launch_lean_nk(const RunArgs &a, cudaStream_t st)
 {
     switch (a.P.scheme) {
@@ -77,11 +77,13 @@ static cudaError_t launch_lean_nk(const RunArgs &a, cudaStream_t st)
 // n_ksub = 3 (every shipped namelist: example.namelist:30, optimization.namelist, tools.py:31) is a compile-time
 // constant of its own instantiation: the three sub-steps share one set of constant loads.
 // Daily output: 24 warps x 80 registers.  Period means (8 accumulators more per thread): 20 warps x 96 registers.
-static cudaError_t launch_lean(const RunArgs &a, cudaStream_t st, bool ext)
+static cudaError_t launch_lean(const RunArgs &a, cudaStream_t st, int ext)
 {
-    if (ext) {                                   // external tsurf / alb rows: daily output only
-        if (a.P.n_ksub == 3) return launch_lean_nk<24, 3, 3, false, true>(a, st);
-        return launch_lean_nk<24, 2, 0, false, true>(a, st);
+    if (ext == 2)                                // any boundary flags: GENERIC physics, scheme resolved at run time
+        return launch_lean_one<SCHEME_RUNTIME, 16, 2, 0, false, 2>(a, st);
+    if (ext == 1) {                              // external tsurf / alb rows: daily output only
+        if (a.P.n_ksub == 3) return launch_lean_nk<24, 3, 3, false, 1>(a, st);
+        return launch_lean_nk<24, 2, 0, false, 1>(a, st);
     }
     if (a.out != nullptr && a.avg_days > 1) {
         if (a.P.n_ksub == 3) return launch_lean_nk<20, 3, 3, true>(a, st);

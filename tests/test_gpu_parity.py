@@ -173,11 +173,13 @@ def test_lean_kernel_random_shapes_against_the_bitmap_kernel():
             assert np.array_equal(res[0][1], res[1][1]), tag
 
 
-@pytest.mark.parametrize("names", [("tsurf",), ("alb",), ("tsurf", "alb")])
+@pytest.mark.parametrize("names", [("tsurf",), ("alb",), ("tsurf", "alb"), ("melt",), ("acc", "smb"), ("shf", "lhf"),
+                                   ("tsurf", "alb", "melt", "refr", "amp"), ("smb", "tsurf")])
 @pytest.mark.parametrize("k", [3, 4])
 def test_lean_kernel_with_external_tsurf_and_alb(names, k):
     """BASELINE configs[3]: isba with bnd%tsurf / bnd%alb fed from an external series runs the plain path with two more
-    rows per stage; bit-identical to the general kernel (9-row run) and within 1e-10 of the oracle"""
+    rows per stage; every other flag set runs the GENERIC physics on the same shell (k_run_lean<EXT = 2>); both are
+    bit-identical to the general kernel (9-row run) and within 1e-10 of the oracle"""
     from semic_b200 import engine
     g = _gpu()
     nx, nwin, ndays = 1024 + 99, 40, 150
@@ -185,6 +187,12 @@ def test_lean_kernel_with_external_tsurf_and_alb(names, k):
     r = np.random.default_rng(5)
     mask = r.choice(np.array([2, 1, 0], dtype=np.int32), size=nx, p=[0.85, 0.10, 0.05]).astype(np.int32)
     S0, m0 = util.init_slab(nx, mask)
+    S0[util.ob.FIDX["amp"]] = 2.5          # consulted when bnd%amp
+    S0[util.ob.FIDX["shf"]] = 3.0          # frozen when bnd%shf
+    S0[util.ob.FIDX["lhf"]] = -2.0
+    S0[util.ob.FIDX["subl"]] = 1e-9        # divided by rhow every sub-step under bnd%lhf (Q3)
+    S0[util.ob.FIDX["refr"]] = 1e-9
+    S0[util.ob.FIDX["smb_snow"]] = 2e-9    # frozen when bnd%smb
     par = dict(util.PAR_ISBA, n_ksub=k)
     # external series: a plain run's own daily output over the window (tsurf <= t0 over snow, alb in [0, 1])
     _, ext, _, _ = g.run_gpu(S0, m0, par, (), forc, nwin, out_days=nwin, branch=False)

@@ -25,12 +25,13 @@ par.tsticsub = par.tstic / 3
 vali = engine.Series(N, 8, W)
 bnd0 = sp.Boundary_Opt_Class()
 engine.run(st, par, bnd0, forcing, W, out=vali, out_days=W)
-for names in ((), ("tsurf",), ("tsurf", "alb")):
+sets = [(), ("tsurf",), ("tsurf", "alb")] + ([("melt",), ("acc", "smb"), ("shf", "lhf"), ("tsurf", "alb", "melt", "acc", "smb")] if os.environ.get("C4_ALL") else [])
+for names in sets:
     bnd = sp.Boundary_Opt_Class()
     sp.surface_boundary_define(bnd, list(names))
     ts = [engine.run(st, par, bnd, forcing, days, vali=vali if names else None, out=out, out_days=days) for _ in range(steps)]
     t = statistics.mean(ts[2:])
-    nbytes = 136 + 8 * len(names)
+    nbytes = 136 + 8 * len([n for n in names if n in ('tsurf', 'alb', 'melt', 'acc', 'smb')])
     rate = N * days / t / 1e6
     print("C4 isba overrides=%-14s %.2f ms  %.2f G pt-days/s  %d B/pt-day -> %.0f GB/s (%.3f of the HBM roof)"
           % ("+".join(names) or "none", t, rate, nbytes, rate * nbytes, rate * nbytes / 6458.7), flush=True)
