@@ -675,6 +675,35 @@ def test_run_host_equals_run(slice_pts, monkeypatch):
     ho.free()
 
 
+@pytest.mark.parametrize("names", [("tsurf", "alb"), ("melt", "acc")])
+def test_run_host_with_external_fields_equals_run(names, monkeypatch):
+    """host-streamed run with boundary overrides fed from a HOST validation window (point slices + day chunks)"""
+    from semic_b200 import engine
+    from semic_b200 import surface_physics as spm
+    g = _gpu()
+    monkeypatch.setenv("SEMIC_HOST_SLICE", "1024")
+    nx, nwin, ndays = 2500, 12, 31
+    forc = util.random_forcing(nx, nwin, seed=51)
+    mask = np.full(nx, 2, dtype=np.int32)
+    mask[::6] = 1
+    S0, m0 = util.init_slab(nx, mask)
+    par_d = dict(util.PAR_ISBA, n_ksub=3)
+    _, ext, _, _ = g.run_gpu(S0, m0, par_d, (), forc, nwin, out_days=nwin, branch=False)
+    ext = np.ascontiguousarray(ext)
+    fin_a, out_a, _, _ = g.run_gpu(S0, m0, par_d, names, forc, ndays, vali=ext, out_days=ndays, branch=False)
+    st = g.make_state(S0, m0)
+    hf = engine.PinnedArray((nwin, 9, nx)); hf.array[...] = forc
+    hv = engine.PinnedArray((nwin, 8, nx)); hv.array[...] = ext
+    ho = engine.PinnedArray((ndays, 8, nx))
+    engine.run_host(st, g.make_par(par_d), g.make_bnd(names), hf.array, ndays, h_vali=hv.array, h_out=ho.array,
+                    out_days=ndays, chunk_days=5)
+    st.download()
+    assert np.array_equal(st.as_slab()[:23], fin_a[:23])
+    assert np.array_equal(out_a, ho.array)
+    spm.surface_dealloc(st)
+    hf.free(); hv.free(); ho.free()
+
+
 # ------------------------------------------------------------------------------------------------------------
 # size-independent properties at large N (BASELINE sizes are too big for the oracle)
 # ------------------------------------------------------------------------------------------------------------
