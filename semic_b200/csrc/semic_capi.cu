@@ -422,7 +422,7 @@ static void g13_6(double x, char *out)
         if (std::fabs(m) >= 0.9999995) { m /= 10.0; ++e; }
         char tmp[64];
         snprintf(tmp, sizeof tmp, "%.6fE%c%02d", m, e < 0 ? '-' : '+', std::abs(e));
-        snprintf(out, 32, "%13s", tmp);
+        snprintf(out, 32, "%13.31s", tmp);
     } else {
         int k = ax == 0.0 ? 1 : (int)std::floor(std::log10(ax)) + 1;      // digits before the point
         if (ax != 0.0 && ax >= std::pow(10.0, k) - 0.5 * std::pow(10.0, k - 6)) ++k;
