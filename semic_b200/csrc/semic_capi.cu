@@ -851,6 +851,7 @@ extern "C" int semic_run(semic_state *now, const semic_par *par, const semic_bnd
                   out ? out->ndays : 1, out ? out->nvar : SEMIC_NOUT, out_days);
     const bool generic = any_consulted_flag(bnd) || par->n_ksub < 1;
     const int strict = opts ? opts->strict : 0;
+    if (!strict) CU(prepare_fast());
     a.avg_days = (opts && out_days > 0 && opts->avg_days > 1) ? opts->avg_days : 0;
     if (a.avg_days > 1) {
         if (generic || strict || out->nvar != SEMIC_NOUT) {
@@ -957,6 +958,7 @@ extern "C" int semic_run_host(semic_state *now, const semic_par *par, const semi
     CUX(cudaEventCreate(&t0));
     CUX(cudaEventCreate(&t1));
 
+    if (!strict) CUX(prepare_fast());
     const int nchunks = (ndays + chunk_days - 1) / chunk_days;
     const int out_first = ndays - out_days;
     CUX(cudaEventRecord(t0, now->stream));

@@ -105,6 +105,9 @@ struct EnsArgs {
     int           uni_ksub;     // the n_ksub all particles share, or 0
 };
 
+// one-time per-device set-up of the fast arithmetic (the 2^(j/2048) table); cheap no-op afterwards.  The launchers call it
+// themselves; timed entry points call it before their first event so that it never lands inside a timed region
+cudaError_t prepare_fast();
 // implemented once per arithmetic mode (semic_kernels_fast.cu / semic_kernels_strict.cu)
 cudaError_t launch_run_fast(const RunArgs &a, bool generic, cudaStream_t st, int *launches);
 cudaError_t launch_run_strict(const RunArgs &a, bool generic, cudaStream_t st, int *launches);
