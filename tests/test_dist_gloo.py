@@ -90,3 +90,21 @@ def test_finish_costs_nan_maps_to_max():
     pop = [{"id": 3, "pos": []}, {"id": 9, "pos": []}]
     c = driver.finish_costs(pop, np.array([4.0, np.nan]))
     assert c[3] == 2.0 and c[9] == np.finfo("d").max            # optimize/tools.py:62
+
+
+def test_reference_arm_under_torchrun_prints_one_json_line():
+    """`bench.py --impl reference` launched like our own arm (torchrun, 2 ranks): rank 0 alone runs the CPU reference and
+    prints exactly one JSON line; the other rank exits 0 without work"""
+    import json
+    import subprocess
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+           "--master-port", str(_free_port()), os.path.join(ROOT, "bench.py"), "--impl", "reference", "--gpus", "2", "--steps", "1",
+           "--warmup", "0", "--cpu-points-per-core", "256", "--cpu-days", "5"]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=600, cwd=ROOT)
+    assert r.returncode == 0, r.stderr[-2000:]
+    lines = [l for l in r.stdout.splitlines() if l.strip()]
+    assert len(lines) == 1, lines
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["metric"] == "grid-point-days/s" and d["value"] > 0
+    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1
+    assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["d2h_bytes_per_step"] == 0 and d["gpu_launches"] == 0
