@@ -2,7 +2,7 @@
 """bench.py -- grid-point-days/s of the SEMIC time step on B200 (BASELINE.json metric).
 
   python bench.py --gpus N --steps K --warmup W          # our arm (CUDA, through the C-ABI)
-  python bench.py --impl reference --gpus N ...          # the reference's CPU implementation (oracle port)
+  python bench.py --impl reference --gpus N ...          # the reference's CPU implementation (oracle/_ref)
 
 Workload (config.workload): BASELINE.json configs[2] -- synthetic Antarctica-scale grid, 16 777 216 points per
 GPU, slater albedo, daily forcing [day][9][point] resident in HBM as a periodic window; a STEP is one simulated
@@ -106,19 +106,39 @@ class ClockSampler(object):
 # ---------------------------------------------------------------------------------------------------------------
 # CPU arm: the oracle port of the reference, one thread per host core (ctypes releases the GIL)
 # ---------------------------------------------------------------------------------------------------------------
-def cpu_reference_rate(scheme, k, pts_per_core, ndays, reps, cores=None):
-    """Times oracle_run (array-form restatement of surface_physics.f90) on cores x pts_per_core points x ndays days.
-    Returns (point-days/s, cores, seconds of the best repetition)."""
+def cpu_reference_kind():
+    """"reference": oracle/_ref, the reference's own Fortran translated mechanically to C (oracle/f90_to_c.py) and
+    compiled with gcc -O3; "port": the hand-written array-form restatement, only when no _ref build is on the box"""
+    from oracle import ref_binding as rb
+    if os.environ.get("SEMIC_CPU_BASELINE", "") == "port" or not rb.available():
+        return "port"
+    try:
+        rb.lib()
+        return "reference"
+    except Exception:
+        return "port"
+
+
+def cpu_reference_rate(scheme, k, pts_per_core, ndays, reps, cores=None, kind=None):
+    """Times the reference's CPU path (the day loop of example.f90:88-127 around surface_energy_and_mass_balance) on
+    cores x pts_per_core points x ndays days, one thread per core.  Returns (point-days/s, cores, seconds of the best
+    repetition, kind)."""
     from oracle import binding as ob
+    from oracle import ref_binding as rb
     from semic_b200 import synth
+    kind = kind or cpu_reference_kind()
     cores = cores or os.cpu_count() or 1
     nwin = min(ndays, 73)
     stride = 5 if nwin == 73 else 1
-    par = ob.make_par(par_dict(scheme, k))
-    bnd = ob.make_bnd()
-    ob.lib()
+    pd = par_dict(scheme, k)
+    dp = lambda a: a.ctypes.data_as(C.POINTER(C.c_double))
     forc = [np.ascontiguousarray(synth.forcing(pts_per_core, nwin, SEED, point0=c * pts_per_core, daystride=stride)) for c in range(min(cores, 4))]
     jobs = []
+    if kind == "reference":
+        par_r, bnd_r = rb.load_par(pd, (), pts_per_core)
+    else:
+        par, bnd = ob.make_par(pd), ob.make_bnd()
+        ob.lib()
     for c in range(cores):
         S, m = ob.new_state(pts_per_core)
         m[:] = synth.mask(pts_per_core, 7, c * pts_per_core, 0.97, 0.02)
@@ -126,13 +146,17 @@ def cpu_reference_rate(scheme, k, pts_per_core, ndays, reps, cores=None):
         S[ob.FIDX["hsnow"]] = 1.0
         S[ob.FIDX["alb"]] = 0.8
         S[ob.FIDX["alb_snow"]] = 0.8
-        jobs.append((S, m, forc[c % len(forc)], np.zeros((8, 8, pts_per_core))))
+        now = rb.state_from_slab(S, m) if kind == "reference" else None
+        jobs.append((S, m, forc[c % len(forc)], np.zeros((8, 8, pts_per_core)), now))
 
     def work(j):
-        S, m, f, out = j
-        dp = lambda a: a.ctypes.data_as(C.POINTER(C.c_double))
-        ob.lib().oracle_run(dp(S), S.shape[1], m.ctypes.data_as(C.POINTER(C.c_int)), S.shape[1], C.byref(par),
-                            C.byref(bnd), dp(f), None, f.shape[0], f.shape[2], ndays, dp(out), 8, pts_per_core, ndays, None)
+        S, m, f, out, now = j
+        if kind == "reference":
+            rb.lib().ref_run(now._p, par_r._p, bnd_r._p, pts_per_core, dp(f), None, f.shape[0], f.shape[2], ndays,
+                             dp(out), 8, pts_per_core, ndays)
+        else:
+            ob.lib().oracle_run(dp(S), S.shape[1], m.ctypes.data_as(C.POINTER(C.c_int)), S.shape[1], C.byref(par),
+                                C.byref(bnd), dp(f), None, f.shape[0], f.shape[2], ndays, dp(out), 8, pts_per_core, ndays, None)
 
     best = None
     for _ in range(reps):
@@ -144,7 +168,14 @@ def cpu_reference_rate(scheme, k, pts_per_core, ndays, reps, cores=None):
             t.join()
         dt = time.perf_counter() - t0
         best = dt if best is None else min(best, dt)
-    return cores * pts_per_core * ndays / best, cores, best
+    if kind == "reference":
+        for j in jobs:
+            rb.free_state(j[4])
+    return cores * pts_per_core * ndays / best, cores, best, kind
+
+
+CPU_KIND_TEXT = {"reference": "the reference's own surface_physics.f90 translated to C by oracle/f90_to_c.py (oracle/_ref), gcc -O3 -fno-fast-math",
+                 "port": "array-form C oracle of surface_physics.f90, gcc -O3 -fno-fast-math"}
 
 
 def run_reference_arm(args):
@@ -158,18 +189,19 @@ def run_reference_arm(args):
     t0 = time.perf_counter()
     rates = []
     for _ in range(args.steps):
-        r, cores, sec = cpu_reference_rate(args.scheme, k, pts, args.cpu_days, 1)
+        r, cores, sec, kind = cpu_reference_rate(args.scheme, k, pts, args.cpu_days, 1)
         rates.append(r)
     wall = time.perf_counter() - t0
     cores = os.cpu_count() or 1
+    kind = cpu_reference_kind()
     value = float(np.mean(rates))
-    sample = "%d cores x %d points x %d days per step (array-form C oracle, gcc -O3 -fno-fast-math)" % (cores, pts, args.cpu_days)
+    sample = "%d cores x %d points x %d days per step (%s)" % (cores, pts, args.cpu_days, CPU_KIND_TEXT[kind])
     line = {"impl": "reference", "metric": "grid-point-days/s", "value": value, "unit": "point-days/s",
             "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": 1e3 * wall / max(args.steps, 1), "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": workload_config(args, 1),
-            "cpu_baseline": {"value": value, "unit": "point-days/s", "cores": cores, "kind": "port", "sample": sample},
+            "config": workload_config(args, int(os.environ.get("WORLD_SIZE", "1"))),
+            "cpu_baseline": {"value": value, "unit": "point-days/s", "cores": cores, "kind": kind, "sample": sample},
             "e2e": {"value": value, "unit": "point-days/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     _emit(json.dumps(line))
@@ -502,11 +534,10 @@ def main():
             os.sched_setaffinity(0, range(os.cpu_count() or 1))
         except Exception:
             pass
-        r, cores, sec = cpu_reference_rate(args.scheme, args.n_ksub, args.cpu_points_per_core, args.cpu_days, 2)
-        line["cpu_baseline"] = {"value": r, "unit": "point-days/s", "cores": cores, "kind": "port",
-                                "sample": "%d cores x %d points x %d days, best of 2 (array-form C oracle of surface_physics.f90, "
-                                          "gcc -O3 -fno-fast-math -ffp-contract=off; no Fortran compiler in the image)"
-                                          % (cores, args.cpu_points_per_core, args.cpu_days), "seconds": sec}
+        r, cores, sec, kind = cpu_reference_rate(args.scheme, args.n_ksub, args.cpu_points_per_core, args.cpu_days, 2)
+        line["cpu_baseline"] = {"value": r, "unit": "point-days/s", "cores": cores, "kind": kind,
+                                "sample": "%d cores x %d points x %d days, best of 2 (%s)"
+                                          % (cores, args.cpu_points_per_core, args.cpu_days, CPU_KIND_TEXT[kind]), "seconds": sec}
     _emit(json.dumps(line))
     if dist is not None:
         dist.destroy_process_group()

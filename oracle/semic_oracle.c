@@ -1,6 +1,6 @@
 /*
  * semic_oracle.c -- CPU restatement of SEMIC's daily time step.  TEST INFRASTRUCTURE ONLY:
- * see the header of semic_oracle.h (who may load this, and why parity is "unpinned").
+ * see the header of semic_oracle.h (who may load this, and how it is pinned to the reference).
  *
  * All citations are file:line in /root/reference (mkrapp/semic).  One C loop per Fortran
  * whole-array statement, evaluated left to right exactly as written; automatic arrays are

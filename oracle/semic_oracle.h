@@ -5,12 +5,16 @@
  * and bench.py's cpu_baseline / --impl reference legs may load it.  The product library
  * (libsemic_b200.so) never links, loads or calls anything in this directory.
  *
- * PARITY UNPINNED: the reference (mkrapp/semic) ships no golden SEMIC output and no Fortran
- * compiler exists in this image, so this restatement cannot be diffed against a run of the
- * reference itself.  It is pinned instead by (a) statement-by-statement citation of
- * surface_physics.f90, (b) analytic known-answer tests, (c) the independent numpy tripwire
- * vectors recorded in SURVEY.md 8(c) (tests/test_oracle.py), and (d) a second, independently
- * written scalar restatement in Python (tests/pyref.py).
+ * PARITY PINNED (round 2): the reference (mkrapp/semic) is Fortran and the image has no Fortran
+ * compiler, so oracle/f90_to_c.py -- a physics-free source-to-source translator -- turns the
+ * reference's own surface_physics.f90, utils.f90, example.f90 and run_particles.f90 into C at build
+ * time (`make -C oracle ref` -> oracle/_ref/, git-ignored).  tests/test_ref_pin.py demands bit-for-bit
+ * equality between this restatement and that build over 6 schemes x 10 boundary-flag sets x the three
+ * shipped data sets, the corner cases, the elementals, CRMSD, averaging and both translated programs;
+ * tests/golden/ref_*.npy are outputs of the translated reference programs on the shipped data
+ * (tests/golden/make_ref_golden.py) and are reproduced bit for bit (tests/test_oracle.py).  What stays
+ * unpinned: a gfortran build's libm calls and instruction selection, which the translation shares with
+ * this file by construction (same gcc, same glibc).
  *
  * Every loop below is one Fortran whole-array statement (the reference is written in array
  * syntax; gfortran emits one sweep over nx per statement and heap-allocates the automatic

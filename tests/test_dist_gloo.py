@@ -106,5 +106,7 @@ def test_reference_arm_under_torchrun_prints_one_json_line():
     assert len(lines) == 1, lines
     d = json.loads(lines[0])
     assert d["impl"] == "reference" and d["metric"] == "grid-point-days/s" and d["value"] > 0
-    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1
+    from oracle import ref_binding as rb
+    assert d["cpu_baseline"]["kind"] == ("reference" if rb.available() else "port") and d["cpu_baseline"]["cores"] >= 1
+    assert d["config"]["world_size"] == 2            # same config as our arm at N = 2
     assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["d2h_bytes_per_step"] == 0 and d["gpu_launches"] == 0

@@ -38,6 +38,45 @@ def test_known_answers_elementals():
     assert alb.value == 0.6                                                                # clamped at alb_smin
 
 
+def _example_run(pd, nloop):
+    """the oracle driven as example/example.f90:74-79,88-127 drives the module"""
+    forc, _ = util.load_fixture("transect")
+    mask = np.array([1, 1, 1, 2, 2, 2, 2], dtype=np.int32)                    # example.namelist:5
+    S, m = util.init_slab(7, mask, hsnow=5.0, alb=np.float64(np.float32(0.8)))   # Q9: single-precision 0.8
+    out, _ = ob.run(S, m, ob.make_par(pd), ob.make_bnd(), forc, nloop * 365, out_days=365)
+    return out
+
+
+@pytest.mark.parametrize("name,scheme,k,nloop", [("out", None, 3, 100), ("nloop1", None, 3, 1), ("slater", "slater", 3, 2),
+                                                 ("isba", "isba", 3, 2), ("denby", "denby", 3, 2), ("alex", "alex", 3, 2),
+                                                 ("none", "none", 3, 2), ("slater24", "slater", 24, 2)])
+def test_oracle_reproduces_the_reference_golden_vectors(name, scheme, k, nloop):
+    """tests/golden/ref_example_*.npy were written by the reference's own example program (translated by
+    oracle/f90_to_c.py, run in the build container: tests/golden/make_ref_golden.py).  Bit for bit."""
+    gold = np.load(os.path.join(util.GOLDEN, "ref_example_%s.npy" % name))
+    pd = util.PAR_EXAMPLE if scheme is None else dict(util.SCHEME_PARS[scheme], n_ksub=k)
+    out = _example_run(pd, nloop)
+    assert np.array_equal(out.view(np.uint64), gold.view(np.uint64))
+
+
+def test_oracle_reproduces_the_reference_particle_costs():
+    """ref_particles_cost.npy: optimize/run_particles.f90 (translated) on the shipped optimization.namelist, three
+    particles in one process: state carried over from particle to particle (Q14), nloop = 20"""
+    import json
+    gold = np.load(os.path.join(util.GOLDEN, "ref_particles_cost.npy"))
+    pars = json.load(open(os.path.join(util.GOLDEN, "ref_particles_pars.json")))
+    forc, vali = util.load_fixture("transect")
+    S, m = ob.new_state(7)
+    m[:] = [1, 1, 1, 2, 2, 2, 2]                                               # optimization.namelist:5
+    S[ob.FIDX["hsnow"]] = 1.0                                                  # run_particles.f90:77-82
+    S[ob.FIDX["alb"]] = vali[0, 1]
+    S[ob.FIDX["tsurf"]] = vali[0, 0]
+    S[ob.FIDX["alb_snow"]] = vali[0, 1]
+    for i, pd in enumerate(pars):
+        out, _ = ob.run(S, m, ob.make_par(dict(pd, n_ksub=3)), ob.make_bnd(), forc, 20 * 365, vali=vali, out_days=365)
+        assert ob.particle_cost(out, vali) == gold[i]
+
+
 def test_tripwire_vectors_from_survey():
     """vectors of an independent numpy restatement made at survey time."""
     forc, _ = util.load_fixture("transect")
