@@ -236,7 +236,6 @@ def main():
     ap.add_argument("--window", type=int, default=73, help="periodic forcing window resident in HBM (days)")
     ap.add_argument("--window-stride", type=int, default=5, help="window row w holds calendar day w*stride (73 x 5 = one year)")
     ap.add_argument("--ring", type=int, default=32, help="daily-output ring (days); large enough that the ring is not L2-resident")
-    ap.add_argument("--ppt", type=int, default=0)
     ap.add_argument("--e2e-days", type=int, default=8, help="days per end-to-end (host buffers) step")
     ap.add_argument("--e2e-steps", type=int, default=2)
     ap.add_argument("--cpu-points-per-core", type=int, default=65536,
@@ -317,7 +316,7 @@ def main():
 
     def step(i):
         return engine.run(st, par, bnd, forcing, args.days, day0=(i * args.days) % args.window, out=out,
-                          out_days=args.days, ppt=args.ppt)
+                          out_days=args.days)
 
     for i in range(args.warmup):
         step(i)
@@ -362,12 +361,12 @@ def main():
                 hf.array[:, :, c0:c1] = forcing.download(0, wh, c0, c1 - c0)
         ho = engine.PinnedArray((args.e2e_days, 8, N))
         engine.run_host(st, par, bnd, hf.array, min(args.e2e_days, 8), h_out=ho.array[:min(args.e2e_days, 8)],
-                        out_days=min(args.e2e_days, 8), chunk_days=1, ppt=args.ppt)
+                        out_days=min(args.e2e_days, 8), chunk_days=1)
         barrier()
         tot = 0.0
         for _ in range(args.e2e_steps):
             tot += engine.run_host(st, par, bnd, hf.array, args.e2e_days, h_out=ho.array, out_days=args.e2e_days,
-                                   chunk_days=1, ppt=args.ppt)
+                                   chunk_days=1)
         barrier()
         if dist is not None:
             import torch
@@ -426,8 +425,8 @@ def main():
         extra = {}
         # C3 at n_ksub=24 on the same buffers
         par24 = make_par(24, args.scheme)
-        engine.run(st, par24, bnd, forcing, 30, out=out, out_days=30, ppt=args.ppt)
-        t = min(engine.run(st, par24, bnd, forcing, args.days, out=out, out_days=args.days, ppt=args.ppt) for _ in range(2))
+        engine.run(st, par24, bnd, forcing, 30, out=out, out_days=30)
+        t = min(engine.run(st, par24, bnd, forcing, args.days, out=out, out_days=args.days) for _ in range(2))
         extra["C3_n_ksub24_point_days_per_s"] = float(N) * args.days / (t * 1e-3)
         extra["C3_n_ksub24_note"] = "same buffers, this rank only; FP64-pipe bound (profiles/r01_summary.md), HBM at ~30 %"
         # C3 with 30-day means instead of daily rows (in-kernel surface_physics_average): 72 + 64/30 B/point-day

@@ -150,7 +150,7 @@ int     semic_state_fill(semic_state *now, int field, double value);
 typedef struct semic_run_opts {
     int strict;        /* 0 = fast math (default), 1 = reference operation order, IEEE div, no FMA contraction */
     int out_days;      /* write daily output for the LAST out_days days of the run (0 = none)       */
-    int ppt;           /* reserved (points per thread; one point per thread measured fastest)         */
+    int reserved0;     /* unused, keep 0 (keeps the layout of round 1)                                */
     int avg_days;      /* > 1: the rows of `out` are the MEANS of the 8 daily fields over consecutive periods
                           of avg_days days of the last out_days days (last period may be shorter) -- the protocol of
                           surface_physics_average (surface_physics.f90:565-629: init / step / end) kept in registers.

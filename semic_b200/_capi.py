@@ -46,7 +46,7 @@ class SemicBnd(C.Structure):
 
 
 class SemicRunOpts(C.Structure):
-    _fields_ = [("strict", C.c_int), ("out_days", C.c_int), ("ppt", C.c_int), ("avg_days", C.c_int), ("reserved", C.c_int * 4)]
+    _fields_ = [("strict", C.c_int), ("out_days", C.c_int), ("reserved0", C.c_int), ("avg_days", C.c_int), ("reserved", C.c_int * 4)]
 
 
 class SemicError(RuntimeError):

@@ -594,6 +594,9 @@ extern "C" int semic_series_alloc(semic_series **out, int npts, int nvar, int nd
     const size_t bytes = (size_t)ndays * nvar * s->ld * sizeof(double);
     if ((e = cudaMalloc(&s->d, bytes)) != cudaSuccess) { delete s; return cuda_fail(e, "series_alloc: cudaMalloc"); }
     if ((e = cudaMemset(s->d, 0, bytes)) != cudaSuccess) { cudaFree(s->d); delete s; return cuda_fail(e, "series_alloc: memset"); }
+    // the fill runs on the legacy stream; the kernels that read the series run on non-blocking streams, which are not
+    // ordered behind it: finish it here
+    if ((e = cudaDeviceSynchronize()) != cudaSuccess) { cudaFree(s->d); delete s; return cuda_fail(e, "series_alloc: sync"); }
     *out = s;
     return SEMIC_OK;
 }
@@ -953,6 +956,7 @@ extern "C" int semic_run_host(semic_state *now, const semic_par *par, const semi
         CUX(cudaEventCreateWithFlags(&ev_k[b], cudaEventDisableTiming));
         CUX(cudaEventCreateWithFlags(&ev_o[b], cudaEventDisableTiming));
     }
+    CUX(cudaDeviceSynchronize());                 // the legacy-stream memsets above are not ordered before the non-blocking streams
     CUX(cudaStreamCreateWithFlags(&s_in, cudaStreamNonBlocking));
     CUX(cudaStreamCreateWithFlags(&s_out, cudaStreamNonBlocking));
     CUX(cudaEventCreate(&t0));

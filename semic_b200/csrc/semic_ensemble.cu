@@ -70,13 +70,14 @@ extern "C" int semic_ensemble_cost(const semic_state *init, const semic_par *par
     a.ntiles = (npts + 31) / 32;
     if (npts > 0) {
         CUE(cudaMalloc(&d_invvar, (size_t)4 * ld * sizeof(double)));
-        CUE(cudaMemset(d_invvar, 0, (size_t)4 * ld * sizeof(double)));
+        CUE(cudaMemsetAsync(d_invvar, 0, (size_t)4 * ld * sizeof(double), st));   // on the stream the kernels run on
         CUE(cudaMalloc(&d_partial, (size_t)npar * a.ntiles * sizeof(double)));
     }
     CUE(cudaMalloc(&d_sumsq, (size_t)npar * sizeof(double)));
-    CUE(cudaMemset(d_sumsq, 0, (size_t)npar * sizeof(double)));
+    CUE(cudaMemsetAsync(d_sumsq, 0, (size_t)npar * sizeof(double), st));
     CUE(cudaMalloc(&d_pars, (size_t)npar * sizeof(DevPar)));
-    CUE(cudaMemcpy(d_pars, hp.data(), (size_t)npar * sizeof(DevPar), cudaMemcpyHostToDevice));
+    CUE(cudaMemcpyAsync(d_pars, hp.data(), (size_t)npar * sizeof(DevPar), cudaMemcpyHostToDevice, st));
+    CUE(cudaStreamSynchronize(st));                // hp is pageable: staged and landed before the launch below
     CUE(cudaEventCreate(&e0));
     CUE(cudaEventCreate(&e1));
     a.slab0 = d_slab; a.mask = d_mask; a.nx = npts; a.ld = ld;

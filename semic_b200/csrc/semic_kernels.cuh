@@ -277,11 +277,14 @@ DEVI int diurnal_cycle(double amp, double tmean, double &above, double &below)
 }
 
 #if !SEMIC_STRICT
-// The same for the fast arithmetic mode: the quotients by amp and amp*amp are multiplications by reciprocals the caller
-// provides (host constants unless bnd%amp makes amp a field), acos/sqrt are the helpers above, and `above` leaves
-// clamped at 0 (the reference clamps it two lines later, :254).  The interior sums keep the reference's unfused order
-// for the reason given above.  tmean*inv_amp is not the IEEE quotient, so |r| is kept below 1 explicitly (IEEE
-// division of |tmean| < amp cannot round to 1); likewise 1 - tmean^2/amp^2 is kept at >= 0.
+// The same for the fast arithmetic mode.  `above` leaves clamped at 0 (the reference clamps it two lines later, :254).
+// The interior branch (taken on the days around melt, ~1/4 of all) is ill-conditioned towards tmean -> -amp: with
+// x = pi - acos(r) -> 0 the numerator of `above` cancels to amp*x^3/2, and an error e in tmp2 = sqrt(1 - tmean^2/amp^2)
+// reaches `above` as amp*e/x.  The reference's tmp2 is a chain of correctly rounded operations, so it is reproduced BIT FOR
+// BIT here: the two quotients are the reciprocal products corrected by one Newton step on the exact remainder
+// (q = q0 + (n - q0*d)*(1/d): the correctly rounded quotient; 2 FMA each instead of the ~20-instruction IEEE division
+// routine), the products and sums are the reference's own unfused sequence, sqrt is IEEE.  What is left against the
+// reference is acos (facos vs glibc, <= 1-2 ulp of a number in (0, pi)), the same as in strict mode.
 DEVI int diurnal_cycle_fast(const double amp, const double inv_amp, const double inv_amp2, const double tmean,
                             double &above, double &below)
 {
@@ -293,11 +296,16 @@ DEVI int diurnal_cycle_fast(const double amp, const double inv_amp, const double
     above = tmean;
     below = 0.0;
     if (fabs(tmean) < amp) {                        // :465
-        double r = tmean * inv_amp;
-        if (!(fabs(r) < 1.0)) r = copysign(0x1.fffffffffffffp-1, tmean);
-        const double tmp1 = facos(r);                                                                   // :455
-        const double w = __dsub_rn(1.0, __dmul_rn(__dmul_rn(tmean, tmean), inv_amp2));                 // :456
-        const double tmp2 = sqrt(dmax1(w, 0.0));
+        const double r0 = tmean * inv_amp;
+        const double r = fma(fma(-r0, amp, tmean), inv_amp, r0);                                        // tmean/amp, :454-455
+        double tmp1 = 0.0, tmp2 = 0.0;                                                                  // :452-453
+        if (fabs(r) < 1.0) {                                                                            // :454
+            tmp1 = facos(r);                                                                            // :455
+            const double t2 = __dmul_rn(tmean, tmean), a2 = __dmul_rn(amp, amp);
+            const double q0 = t2 * inv_amp2;
+            const double q = fma(fma(-q0, a2, t2), inv_amp2, q0);                                       // tmean**2/amp**2
+            tmp2 = sqrt(__dsub_rn(1.0, q));                                                             // :456
+        }
         const double at2 = __dmul_rn(amp, tmp2);
         above = __dadd_rn(__dadd_rn(__dmul_rn(-tmean, tmp1), at2), __dmul_rn(ka[12], tmean)) * frcp(__dsub_rn(ka[12], tmp1));   // :467
         above = dmax1(above, 0.0);

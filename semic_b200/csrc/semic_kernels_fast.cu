@@ -51,7 +51,10 @@ static cudaError_t ensure_exp_table()
     if (done[dev]) return cudaSuccess;
     static double host_tab[fast_mode::kExpTab];
     for (int j = 0; j < fast_mode::kExpTab; ++j) host_tab[j] = (double)exp2l((long double)j / (long double)fast_mode::kExpTab);
-    e = cudaMemcpyToSymbol(fast_mode::g_exp2_tab, host_tab, sizeof host_tab);     // synchronous: ordered before any later launch
+    // a pageable-memory copy on the legacy stream may return before the DMA has landed, and the kernels that read the
+    // table run on non-blocking streams (not ordered behind the legacy stream): wait for it before declaring it done
+    e = cudaMemcpyToSymbol(fast_mode::g_exp2_tab, host_tab, sizeof host_tab);
+    if (e == cudaSuccess) e = cudaDeviceSynchronize();
     if (e == cudaSuccess) done[dev] = true;
     return e;
 }

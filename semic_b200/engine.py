@@ -55,13 +55,12 @@ class Series(object):
             pass
 
 
-def run(state, par, bnd, forcing, ndays, vali=None, day0=0, out=None, out_days=0, strict=False, ppt=0, avg_days=0):
+def run(state, par, bnd, forcing, ndays, vali=None, day0=0, out=None, out_days=0, strict=False, avg_days=0):
     """semic_run: ndays days of the persistent kernel on device-resident forcing.  Returns kernel ms.
     avg_days > 1: rows of `out` are means over consecutive periods of avg_days days (in-kernel surface_physics_average)."""
     opts = SemicRunOpts()
     opts.strict = 1 if strict else 0
     opts.out_days = int(out_days)
-    opts.ppt = int(ppt)
     opts.avg_days = int(avg_days)
     ms = C.c_float(0.0)
     check(lib().semic_run(state.handle, C.byref(par._c), C.byref(bnd._c), forcing.handle,
@@ -97,7 +96,7 @@ class PinnedArray(object):
             pass
 
 
-def run_host(state, par, bnd, h_forcing, ndays, h_vali=None, h_out=None, out_days=0, chunk_days=8, strict=False, ppt=0):
+def run_host(state, par, bnd, h_forcing, ndays, h_vali=None, h_out=None, out_days=0, chunk_days=8, strict=False):
     """semic_run_host: forcing [nwin][9][ldh] (and vali [nwin][8][ldh]) live in HOST memory (numpy arrays or
     PinnedArray.array); H2D, kernel and D2H are pipelined in chunks of chunk_days.  Returns total ms."""
     nwin, nine, ldh = h_forcing.shape
@@ -108,7 +107,6 @@ def run_host(state, par, bnd, h_forcing, ndays, h_vali=None, h_out=None, out_day
         assert h_out is not None and h_out.shape == (out_days, NOUT, ldh) and h_out.flags.c_contiguous
     opts = SemicRunOpts()
     opts.strict = 1 if strict else 0
-    opts.ppt = int(ppt)
     ms = C.c_float(0.0)
     check(lib().semic_run_host(state.handle, C.byref(par._c), C.byref(bnd._c), h_forcing.ctypes.data,
                                h_vali.ctypes.data if h_vali is not None else None, nwin, ldh, int(ndays),

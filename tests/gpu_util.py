@@ -37,7 +37,7 @@ def make_state(slab, mask):
     return st
 
 
-def run_gpu(slab, mask, par_d, bnd_names, forcing, ndays, vali=None, out_days=0, strict=False, ppt=0, branch=True):
+def run_gpu(slab, mask, par_d, bnd_names, forcing, ndays, vali=None, out_days=0, strict=False, branch=True):
     """Runs semic_run on copies of the inputs.  Returns (final slab (31,nx), out [out_days][8][nx], branch uint8, ms)."""
     nx = slab.shape[1]
     par = make_par(par_d)
@@ -46,7 +46,7 @@ def run_gpu(slab, mask, par_d, bnd_names, forcing, ndays, vali=None, out_days=0,
     fs = engine.Series(nx, 9, forcing.shape[0]).upload(forcing)
     vs = engine.Series(nx, 8, vali.shape[0]).upload(vali) if vali is not None else None
     outs = engine.Series(nx, 9 if branch else 8, out_days) if out_days > 0 else None
-    ms = engine.run(st, par, bnd, fs, ndays, vali=vs, out=outs, out_days=out_days, strict=strict, ppt=ppt)
+    ms = engine.run(st, par, bnd, fs, ndays, vali=vs, out=outs, out_days=out_days, strict=strict)
     st.download()
     final = st.as_slab()
     out = br = None

@@ -8,17 +8,17 @@ from tests import util, gpu_util
 BITS = ["ts<t0", "clamp", "gate", "diurnal_lo", "diurnal_hi", "melt>0", "hsnow==0", "snow2ice"]
 
 
-def report(label, par, forc, mask, ndays, strict, ppt=0, vali=None, bnd=()):
+def report(label, par, forc, mask, ndays, strict, vali=None, bnd=()):
     nx = forc.shape[2]
     S0, m0 = util.init_slab(nx, mask)
-    fin_g, out_g, br_g, ms = gpu_util.run_gpu(S0, m0, par, bnd, forc, ndays, vali=vali, out_days=ndays, strict=strict, ppt=ppt)
+    fin_g, out_g, br_g, ms = gpu_util.run_gpu(S0, m0, par, bnd, forc, ndays, vali=vali, out_days=ndays, strict=strict)
     fin_o, out_o, br_o = gpu_util.run_oracle(S0, m0, par, bnd, forc, ndays, vali=vali, out_days=ndays)
     diff = br_g ^ br_o
     taint = util.tainted(br_g, br_o)
     oe = util.out_errors(out_g, out_o, exclude=taint)
     oe_all = util.out_errors(out_g, out_o, exclude=taint, pointwise=True)
     se = util.state_errors(fin_g, fin_o, exclude_points=taint.any(axis=0))
-    print("== %s nx=%d days=%d k=%d scheme=%s strict=%d ppt=%d  kernel %.2f ms" % (label, nx, ndays, par["n_ksub"], par["alb_scheme"], strict, ppt, ms))
+    print("== %s nx=%d days=%d k=%d scheme=%s strict=%d  kernel %.2f ms" % (label, nx, ndays, par["n_ksub"], par["alb_scheme"], strict, ms))
     print("   daily field-relative (untainted):", " ".join("%s=%.1e" % kv for kv in oe.items()))
     print("   daily pointwise+floor (untainted):", " ".join("%s=%.1e" % kv for kv in oe_all.items()))
     print("   tainted point-days: %d of %d (%.4f%%) on %d points" % (int(taint.sum()), taint.size, 100.0 * taint.mean(), int(taint.any(axis=0).sum())))

@@ -12,33 +12,41 @@ from tests.util import TOL
 
 pytestmark = pytest.mark.gpu
 
+PW_TOL_FLUX = 1e-9        # pointwise bound of shf / lhf against their 1e-2 W/m2 floor, see _compare
+
 
 def _gpu():
     from tests import gpu_util
     return gpu_util
 
 
-def _compare(par_d, bnd_names, forcing, ndays, mask, vali=None, strict=False, ppt=0, hsnow=1.0, tol=TOL,
+def _compare(par_d, bnd_names, forcing, ndays, mask, vali=None, strict=False, hsnow=1.0, tol=TOL, pw_tol=TOL,
              max_flip_frac=2e-4, label=""):
     g = _gpu()
     nx = forcing.shape[2]
     S0, m0 = util.init_slab(nx, mask, hsnow=hsnow)
     fin_g, out_g, br_g, _ = g.run_gpu(S0, m0, par_d, bnd_names, forcing, ndays, vali=vali, out_days=ndays,
-                                      strict=strict, ppt=ppt)
+                                      strict=strict)
     fin_o, out_o, br_o = g.run_oracle(S0, m0, par_d, bnd_names, forcing, ndays, vali=vali, out_days=ndays)
     nflip, pts, first = util.flip_report(br_g, br_o)
     taint = util.tainted(br_g, br_o)
     oe = util.out_errors(out_g, out_o, exclude=taint)
     se = util.state_errors(fin_g, fin_o, exclude_points=pts)
-    pw = max(util.out_errors(out_g, out_o, exclude=taint, pointwise=True).values())
+    pwv = util.out_errors(out_g, out_o, exclude=taint, pointwise=True)
+    pw = max(pwv.values())
     worst = max(list(oe.values()) + list(se.values()))
-    print("\n[parity %s] nx=%d days=%d k=%d scheme=%s strict=%d: max rel err %.3e (daily %s; pointwise+floor %.1e); "
+    print("\n[parity %s] nx=%d days=%d k=%d scheme=%s strict=%d: max rel err %.3e (daily %s); pointwise+floor %s; "
           "material flips: %d point-days on %d points (%.4f%% of point-days tainted); by bit %s"
-          % (label, nx, ndays, par_d["n_ksub"], par_d["alb_scheme"], strict, worst, max(oe, key=oe.get), pw,
-             nflip, int(pts.sum()), 100.0 * taint.mean(), util.flips_by_bit(br_g, br_o)))
+          % (label, nx, ndays, par_d["n_ksub"], par_d["alb_scheme"], strict, worst, max(oe, key=oe.get),
+             " ".join("%s=%.1e" % kv for kv in pwv.items()), nflip, int(pts.sum()), 100.0 * taint.mean(),
+             util.flips_by_bit(br_g, br_o)))
     assert worst <= tol, (oe, se)
-    # the pointwise metric is ill-conditioned near cancellations (tmean -> -amp, ts -> t2m); keep it bounded anyway
-    assert pw <= 1e-6, pw
+    # The pointwise metric |gpu-ref| / max(|ref|, floor), per variable, on every untainted point-day: 1e-10 as well.
+    # shf and lhf are exchange coefficients times temperature / humidity DIFFERENCES: one ulp of tsurf (5.7e-14 K) times
+    # csh*cap*rhoa*wind (up to 64 W/m2/K in the forcing range) is 3.6e-12 W/m2 = 3.6e-10 of the 1e-2 W/m2 floor, so for
+    # these two the pointwise bound against the floor is 1e-9 (their error relative to the field is bounded by 1e-10 above).
+    for n, e in pwv.items():
+        assert e <= (PW_TOL_FLUX if n in ("shf", "lhf") else pw_tol), (n, e, pwv)
     # Flips are threshold events of single points (a one-ulp ghost snow layer over land keeps the :201 gate on),
     # never a systematic drift: ice points (mask 2) are immune, only land points near complete snow melt flip.
     assert (mask[pts] == 1).all() or pts.sum() <= max(2, int(max_flip_frac * nx)), (mask[pts], pts.sum())
@@ -80,6 +88,43 @@ def test_example_namelist_config1():
     assert d[:3].max() < 0.05          # land points: ghost-snow flips over 100 loops move the annual mean by mK
 
 
+@pytest.mark.parametrize("strict", [False, True])
+@pytest.mark.parametrize("name,scheme,k,nloop", [("out", None, 3, 100), ("nloop1", None, 3, 1), ("slater", "slater", 3, 2),
+                                                 ("isba", "isba", 3, 2), ("denby", "denby", 3, 2), ("alex", "alex", 3, 2),
+                                                 ("none", "none", 3, 2), ("slater24", "slater", 24, 2)])
+def test_against_reference_golden_vectors(name, scheme, k, nloop, strict):
+    """tests/golden/ref_example_*.npy: example.out as written by the reference's OWN example program (its Fortran translated
+    by oracle/f90_to_c.py and run in the build container on the shipped transect data; tests/golden/make_ref_golden.py).
+    The CUDA path, driven like example.f90:74-127, against those files."""
+    import os
+    gold = np.load(os.path.join(util.GOLDEN, "ref_example_%s.npy" % name))
+    forc, _ = util.load_fixture("transect")
+    mask = np.array([1, 1, 1, 2, 2, 2, 2], dtype=np.int32)
+    pd = util.PAR_EXAMPLE if scheme is None else dict(util.SCHEME_PARS[scheme], n_ksub=k)
+    g = _gpu()
+    S0, m0 = util.init_slab(7, mask, hsnow=5.0, alb=np.float64(np.float32(0.8)))
+    ndays = 365 * nloop
+    fin_g, out_g, br_g, _ = g.run_gpu(S0, m0, pd, (), forc, ndays, out_days=365, strict=strict)
+    fin_o, out_o, br_o = g.run_oracle(S0, m0, pd, (), forc, ndays, out_days=365)
+    assert np.array_equal(out_o.view(np.uint64), gold.view(np.uint64))        # the oracle IS the golden file, bit for bit
+    taint = util.tainted(br_g, br_o)
+    if nloop > 2:
+        # flips before the last year are invisible to its bitmap: a point whose daily fields differ at the 1e-6 level
+        # went through one (land points near complete snow melt); they are reported, not hidden
+        far = (util.rel_err(out_g[:, 0, :], gold[:, 0, :], util.FLOOR["tsurf"]) > 1e-9).any(axis=0)
+        taint = taint | far[None, :]
+        assert (mask[far] == 1).all(), far
+    oe = util.out_errors(out_g, gold, exclude=taint)
+    pwv = util.out_errors(out_g, gold, exclude=taint, pointwise=True)
+    print("\n[golden %s strict=%d] field-relative %s | pointwise %s | tainted %.3f%%"
+          % (name, strict, " ".join("%s=%.1e" % kv for kv in oe.items()), " ".join("%s=%.1e" % kv for kv in pwv.items()),
+             100 * taint.mean()))
+    assert max(oe.values()) <= TOL, oe
+    for n, e in pwv.items():
+        assert e <= (PW_TOL_FLUX if n in ("shf", "lhf") else TOL), (n, e)
+    assert taint.mean() < 0.5
+
+
 def test_c20_ten_years():
     """c20 station: 3652 days of real forcing, single point (mask 2)."""
     forc, _ = util.load_fixture("c20")
@@ -89,8 +134,8 @@ def test_c20_ten_years():
 # ------------------------------------------------------------------------------------------------------------
 # synthetic forcing generated on the device (the bench's generator): oracle consumes the same bytes
 # ------------------------------------------------------------------------------------------------------------
-@pytest.mark.parametrize("k,ppt", [(3, 1), (24, 1), (3, 2)])
-def test_synthetic_one_year(k, ppt):
+@pytest.mark.parametrize("k", [3, 24])
+def test_synthetic_one_year(k):
     from semic_b200 import engine
     nx = 4096 + 333                       # several tiles, ragged tail
     fs = engine.Series(nx, 9, 365).synth_forcing(20260101, point0=0, dayofs=0)
@@ -98,7 +143,7 @@ def test_synthetic_one_year(k, ppt):
     fs.free()
     r = np.random.default_rng(5)
     mask = r.choice(np.array([2, 1, 0], dtype=np.int32), size=nx, p=[0.85, 0.10, 0.05]).astype(np.int32)
-    _compare(dict(util.PAR_SLATER, n_ksub=k), (), forc, 365, mask, ppt=ppt, label="synthetic")
+    _compare(dict(util.PAR_SLATER, n_ksub=k), (), forc, 365, mask, label="synthetic")
 
 
 # ------------------------------------------------------------------------------------------------------------
@@ -777,6 +822,40 @@ def test_ensemble_cost_matches_oracle():
     err = max(abs(cost_gpu[k] - cost_ref[k]) / cost_ref[k] for k in cost_ref)
     print("\n[ensemble] 13 particles x %d points x %d days x %d loops: max rel cost error %.3e" % (nx, ntime, nloop, err))
     assert err <= 1e-9          # one-pass shifted sums on the device vs the reference's two-pass CRMSD
+
+
+def test_ensemble_against_the_reference_run_particles_program():
+    """tests/golden/ref_particles_cost.npy: the cost the reference's own run_particles program (translated, run in the build
+    container) writes for its first particle on the shipped optimization.namelist (transect, nloop = 20, slater flags off).
+    The first particle starts from the initial state of run_particles.f90:77-82, as every particle does here (Q14)."""
+    import json
+    import os
+    from semic_b200 import engine
+    from semic_b200 import surface_physics as spm
+    g = _gpu()
+    gold = np.load(os.path.join(util.GOLDEN, "ref_particles_cost.npy"))
+    pars = json.load(open(os.path.join(util.GOLDEN, "ref_particles_pars.json")))
+    forc, vali = util.load_fixture("transect")
+    st = spm.Surface_State_Class()
+    spm.surface_alloc(st, 7)
+    st.mask = np.array([1, 1, 1, 2, 2, 2, 2], dtype=np.int32)                   # optimization.namelist:5
+    st.hsnow = 1.0                                                              # run_particles.f90:77-82
+    st.hice = 0.0
+    st.alb = vali[0, 1]
+    st.tsurf = vali[0, 0]
+    st.alb_snow = vali[0, 1]
+    st.upload()
+    fs = engine.Series(7, 9, 365).upload(forc)
+    vs = engine.Series(7, 8, 365).upload(vali)
+    plist = [g.make_par(dict(pd, n_ksub=3)) for pd in pars]
+    sumsq, _ = engine.ensemble_cost(st, plist, spm.Boundary_Opt_Class(), fs, vs, 365, 20)
+    cost = np.sqrt(sumsq)
+    fs.free(); vs.free(); spm.surface_dealloc(st)
+    print("\n[ensemble vs reference program] cost %r reference %r" % (cost.tolist(), gold.tolist()))
+    assert abs(cost[0] - gold[0]) <= 1e-9 * gold[0]
+    # particles 1, 2 of the reference inherit the final state of their predecessor (Q14, documented deviation): after 20
+    # spin-up loops the memory of the start state is small but not zero
+    assert np.all(np.abs(cost[1:] - gold[1:]) <= 5e-2 * gold[1:])
 
 
 @pytest.mark.parametrize("case", ["same_scheme_mixed_k", "mixed_scheme_k3", "mixed_both"])

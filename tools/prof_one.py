@@ -1,4 +1,4 @@
-"""One configuration of k_run for ncu: python tools/prof_one.py <points> <days> <k> [ppt] [launches]"""
+"""One configuration of k_run for ncu: python tools/prof_one.py <points> <days> <k> [unused] [launches]"""
 import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import bench
@@ -6,7 +6,6 @@ from semic_b200 import engine, surface_physics as sp
 from semic_b200._capi import FIELD_ID, check, lib
 
 N = int(sys.argv[1]); days = int(sys.argv[2]); k = int(sys.argv[3])
-ppt = int(sys.argv[4]) if len(sys.argv) > 4 else 0
 nl = int(sys.argv[5]) if len(sys.argv) > 5 else 3
 L = lib()
 st = sp.Surface_State_Class(); sp.surface_alloc(st, N)
@@ -22,5 +21,5 @@ for key, v in bench.par_dict("slater", k).items():
     setattr(par, key, v)
 par.tsticsub = par.tstic / k
 for i in range(nl):
-    t = engine.run(st, par, bnd, forcing, days, out=out, out_days=days, ppt=ppt)
+    t = engine.run(st, par, bnd, forcing, days, out=out, out_days=days)
     print("launch %d: %.3f ms  %.2f G pt-days/s" % (i, t, N * days / (t * 1e-3) / 1e9), flush=True)

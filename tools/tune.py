@@ -1,4 +1,4 @@
-"""Times k_run variants (SEMIC_MINB x ppt x n_ksub) on one allocation.  python tools/tune.py [points] [days]"""
+"""Times k_run variants (SEMIC_SHAPE x n_ksub) on one allocation.  python tools/tune.py [points] [days]"""
 import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import bench
