@@ -4,12 +4,14 @@
   python bench.py --gpus N --steps K --warmup W          # our arm (CUDA, through the C-ABI)
   python bench.py --impl reference --gpus N ...          # the reference's CPU implementation (oracle/_ref)
 
-Workload (config.workload): BASELINE.json configs[2] -- synthetic Antarctica-scale grid, 16 777 216 points per
-GPU, slater albedo, daily forcing [day][9][point] resident in HBM as a periodic window; a STEP is one simulated
-year (365 days) of `surface_energy_and_mass_balance` over every point, with the 8 daily output fields the
-reference drivers emit written to a ring (output mode M1, 136 algorithmic bytes per point-day).  `--steps 10`
-is the 10-year run.  Grid points are sharded contiguously over the ranks with no communication ("weak": every
-rank owns --points points).
+Workload (config.workload): BASELINE.json configs[2] -- ONE synthetic Antarctica-scale grid of 16 777 216 points,
+slater albedo, sharded contiguously over the N GPUs with no communication ("strong" scaling: rank r owns points
+[r*P/N, (r+1)*P/N); `--weak` gives every rank --points points instead, and at N > 1 that figure is also reported in
+`extra`).  Daily forcing [day][9][point] is resident in HBM as a periodic window; a STEP is one simulated year
+(365 days) of `surface_energy_and_mass_balance` over every point, with the 8 daily output fields the reference
+drivers emit written to a ring (output mode M1, 136 algorithmic bytes per point-day).  `--steps 10` is the
+10-year run.  At N > 1 every rank also takes part in the parameter ensemble of configs[4] with the library's own
+NCCL communicator (one all-reduce of the per-particle misfit sums).
 
 One JSON line on stdout (rank 0).  See DESIGN.md "Measurement" for the definition of every key.
 """
@@ -65,7 +67,7 @@ class ClockSampler(object):
         self.lines = []
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(gpu_index), "--query-gpu=" + self.Q,
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                          "--format=csv,noheader,nounits", "-lms", "20"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._pump, daemon=True)
             self.t.start()
@@ -209,11 +211,12 @@ def run_reference_arm(args):
 
 
 def workload_config(args, world):
-    per_gpu = args.points // world if getattr(args, "strong", False) else args.points
-    return {"workload": "C3 synthetic Antarctica-scale grid: %d points/GPU x 365 days/step, slater-family scheme '%s', "
+    strong = not getattr(args, "weak", False)
+    per_gpu = args.points // world if strong else args.points
+    return {"workload": "C3 synthetic Antarctica-scale grid: %d points in all (%d per GPU) x 365 days/step, slater-family scheme '%s', "
                         "n_ksub=%d, daily output M1 (8 fields), forcing window %d days resident in HBM"
-                        % (per_gpu, args.scheme, args.n_ksub, args.window),
-            "points_per_gpu": per_gpu, "days_per_step": args.days, "n_ksub": args.n_ksub, "alb_scheme": args.scheme,
+                        % (per_gpu * world, per_gpu, args.scheme, args.n_ksub, args.window),
+            "points_total": per_gpu * world, "points_per_gpu": per_gpu, "days_per_step": args.days, "n_ksub": args.n_ksub, "alb_scheme": args.scheme,
             "forcing_window_days": args.window, "forcing_window_stride_days": args.window_stride, "output_ring_days": args.ring, "output_mode": "M1",
             "sharding": "contiguous point ranges, no communication", "world_size": world,
             "l2": "inputs (forcing window) far larger than the 126 MB L2; every byte is read once per pass",
@@ -229,7 +232,7 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--points", type=int, default=1 << 24, help="grid points per GPU (C3: 16 777 216)")
+    ap.add_argument("--points", type=int, default=1 << 24, help="grid points of the whole grid (C3: 16 777 216); per GPU with --weak")
     ap.add_argument("--days", type=int, default=365, help="simulated days per step")
     ap.add_argument("--n-ksub", type=int, default=3, help="sub-daily steps (the reference's shipped namelists use 3)")
     ap.add_argument("--scheme", default="slater")
@@ -241,13 +244,15 @@ def main():
     ap.add_argument("--cpu-points-per-core", type=int, default=65536,
                     help="CPU sample: points per host core (26 MB of state+forcing per core: not cache resident, like the full grid)")
     ap.add_argument("--cpu-days", type=int, default=365)
-    ap.add_argument("--strong", action="store_true",
-                    help="strong scaling: --points is the WHOLE grid, sharded contiguously over the ranks (default: weak, --points per GPU)")
+    ap.add_argument("--weak", action="store_true",
+                    help="weak scaling: every rank owns --points points (default: strong, ONE grid of --points points sharded over the ranks)")
+    ap.add_argument("--strong", action="store_true", help="(default now; kept for compatibility)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--extra", action="store_true", help="(default now; kept for compatibility)")
     ap.add_argument("--no-extra", action="store_true", help="skip the extra figures: C3 at n_ksub=24, C2 (100k points, n_ksub=24)")
     args = ap.parse_args()
+    args.strong = not args.weak
 
     if args.impl == "reference":
         return run_reference_arm(args)
@@ -381,48 +386,59 @@ def main():
         hf.free()
         ho.free()
 
-    if rank != 0:
-        if dist is not None:
-            dist.destroy_process_group()
-        return 0
+    def maxr(vals):
+        """max over ranks of each value (device times are always taken as the max over ranks)"""
+        if dist is None:
+            return [float(v) for v in vals]
+        import torch
+        t = torch.tensor([float(v) for v in vals], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return [float(x) for x in t]
+
+    def minr(vals):
+        return [-x for x in maxr([-float(v) for v in vals])]
 
     peaks, peak_src = measured_peaks()
     hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
-    # dominant kernel = k_run (the only kernel in the timed region): algorithmic bytes per launch / mean launch time
-    launch_ms = kernel_ms / max(args.steps, 1)
-    alg_bytes = float(N) * args.days * (B_FORCING + B_OUT)
-    achieved = alg_bytes / (launch_ms * 1e-3) / 1e9
-    traffic = None
-    tp = os.path.join(ROOT, "profiles", "traffic.json")
-    if os.path.exists(tp):
-        try:
-            tj = json.load(open(tp))
-            key = "k%d" % args.n_ksub
-            if key in tj and tj[key].get("bytes_per_point_day") is not None:
-                traffic = tj[key]["bytes_per_point_day"] * float(N) * args.days
-        except Exception:
-            traffic = None
-    roofline = {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
-                "traffic": traffic, "peak_source": peak_src, "kernel": "k_run_lean (persistent multi-day step)",
-                "algorithmic_bytes_per_point_day": B_FORCING + B_OUT, "launch_ms": launch_ms}
-    # second denominator: the path is FP64-pipe / issue bound for larger n_ksub -- measured DFMA peak
-    ms = C.c_float(0.0)
-    fl = C.c_double(0.0)
-    L.semic_probe_dfma(1 << 14, C.byref(ms), C.byref(fl))
-    check(L.semic_probe_dfma(1 << 16, C.byref(ms), C.byref(fl)))
-    dfma_tflops = fl.value / (ms.value * 1e-3) / 1e12
-    roofline["fp64_dfma_peak_tflops_measured"] = dfma_tflops
+    line = None
+    extra = {}
+    if rank == 0:
+        # dominant kernel = k_run (the only kernel in the timed region): algorithmic bytes per launch / mean launch time
+        launch_ms = kernel_ms / max(args.steps, 1)
+        alg_bytes = float(N) * args.days * (B_FORCING + B_OUT)
+        achieved = alg_bytes / (launch_ms * 1e-3) / 1e9
+        traffic = None
+        tp = os.path.join(ROOT, "profiles", "traffic.json")
+        if os.path.exists(tp):
+            try:
+                tj = json.load(open(tp))
+                key = "k%d" % args.n_ksub
+                if key in tj and tj[key].get("bytes_per_point_day") is not None:
+                    traffic = tj[key]["bytes_per_point_day"] * float(N) * args.days
+            except Exception:
+                traffic = None
+        roofline = {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
+                    "traffic": traffic, "peak_source": peak_src, "kernel": "k_run_lean (persistent multi-day step)",
+                    "algorithmic_bytes_per_point_day": B_FORCING + B_OUT, "launch_ms": launch_ms}
+        # second denominator: the path is FP64-pipe / issue bound for larger n_ksub (SURVEY 8d) -- measured DFMA peak
+        ms = C.c_float(0.0)
+        fl = C.c_double(0.0)
+        L.semic_probe_dfma(1 << 14, C.byref(ms), C.byref(fl))
+        check(L.semic_probe_dfma(1 << 16, C.byref(ms), C.byref(fl)))
+        dfma_tflops = fl.value / (ms.value * 1e-3) / 1e12
+        roofline["fp64_dfma_peak_tflops_measured"] = dfma_tflops
 
-    line = {"metric": "grid-point-days/s", "value": value, "unit": "point-days/s", "n_gpus": world, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": kernel_ms / max(args.steps, 1), "higher_is_better": True,
-            "scaling": "strong" if args.strong else "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": workload_config(args, world), "roofline": roofline, "gpu_launches": launches,
-            "wall_ms_per_step": wall_ms / max(args.steps, 1), "clocks": clocks}
-    if e2e is not None:
-        line["e2e"] = e2e
+        line = {"metric": "grid-point-days/s", "value": value, "unit": "point-days/s", "n_gpus": world, "steps": args.steps,
+                "warmup": args.warmup, "ms_per_step": kernel_ms / max(args.steps, 1), "higher_is_better": True,
+                "scaling": "strong" if args.strong else "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+                "config": workload_config(args, world), "roofline": roofline, "gpu_launches": launches,
+                "wall_ms_per_step": wall_ms / max(args.steps, 1), "clocks": clocks}
+        if e2e is not None:
+            line["e2e"] = e2e
 
-    if not args.no_extra:
-        extra = {}
+
+    # ---- rank 0 only, on the headline buffers (the other ranks wait at the next barrier) ----
+    if rank == 0 and not args.no_extra:
         # C3 at n_ksub=24 on the same buffers
         par24 = make_par(24, args.scheme)
         engine.run(st, par24, bnd, forcing, 30, out=out, out_days=30)
@@ -439,10 +455,145 @@ def main():
             means.free()
         except Exception as e:
             extra["C3_monthly_means_error"] = str(e)[:200]
-        # the big C3 buffers are done: release them before the other configurations allocate theirs
-        forcing.free()
-        out.free()
-        sp.surface_dealloc(st)
+        # the strict arithmetic (reference operation order, IEEE division, libdevice exp/acos/pow): the cost of exactness
+        try:
+            engine.run(st, par, bnd, forcing, 30, out=out, out_days=30, strict=True)
+            t = min(engine.run(st, par, bnd, forcing, args.days, out=out, out_days=args.days, strict=True) for _ in range(2))
+            extra["C3_strict_point_days_per_s"] = float(N) * args.days / (t * 1e-3)
+            extra["C3_strict_note"] = "n_ksub=%d, same buffers, this rank only; strict mode is <= 1e-13 field-relative vs the oracle" % args.n_ksub
+        except Exception as e:
+            extra["C3_strict_error"] = str(e)[:200]
+    # the big C3 buffers are done: release them before the other configurations allocate theirs
+    forcing.free()
+    out.free()
+    sp.surface_dealloc(st)
+    barrier()
+
+    # ---- legs every rank takes part in ----
+    if not args.no_extra:
+        if world > 1 and args.strong:
+            # (a) weak scaling beside the strong headline: 16.7 M points PER GPU, same protocol
+            try:
+                Nw = args.points
+                stw = make_state(Nw, rank * Nw)
+                fw = engine.Series(Nw, 9, args.window).synth_forcing(SEED, point0=rank * Nw, dayofs=0, daystride=args.window_stride)
+                ow = engine.Series(Nw, 8, args.ring)
+                engine.run(stw, par, bnd, fw, args.days, out=ow, out_days=args.days)
+                barrier()
+                ms = sum(engine.run(stw, par, bnd, fw, args.days, day0=((i + 1) * args.days) % args.window, out=ow,
+                                    out_days=args.days) for i in range(3))
+                barrier()
+                ms = maxr([ms])[0]
+                extra["C3_weak_point_days_per_s"] = float(Nw) * world * args.days * 3 / (ms * 1e-3)
+                extra["C3_weak_note"] = "%d points PER GPU (the round-1 protocol), 3 steps, max over ranks" % Nw
+                for x in (fw, ow):
+                    x.free()
+                sp.surface_dealloc(stw)
+            except Exception as e:
+                extra["C3_weak_error"] = str(e)[:200]
+            barrier()
+        if args.strong and float(N) * 365 * B_FORCING <= 100e9:
+            # (b) the whole year of forcing resident (441 GB over the GPUs; 55 GB per GPU at N = 8): no window
+            try:
+                sty = make_state(N, p0)
+                fy = engine.Series(N, 9, 365).synth_forcing(SEED, point0=p0, dayofs=0, daystride=1)
+                oy = engine.Series(N, 8, args.ring)
+                engine.run(sty, par, bnd, fy, 365, out=oy, out_days=365)
+                barrier()
+                ms = sum(engine.run(sty, par, bnd, fy, 365, out=oy, out_days=365) for _ in range(3))
+                barrier()
+                ms = maxr([ms])[0]
+                extra["C3_strong_full_year_resident_point_days_per_s"] = float(args.points) * 365 * 3 / (ms * 1e-3)
+                extra["C3_strong_full_year_resident_note"] = ("365 forcing rows resident per GPU (%.1f GB), %d points per GPU, 3 steps, max over ranks"
+                                                              % (float(N) * 365 * B_FORCING / 1e9, N))
+                for x in (fy, oy):
+                    x.free()
+                sp.surface_dealloc(sty)
+            except Exception as e:
+                extra["C3_full_year_error"] = str(e)[:200]
+            barrier()
+        # (c) configs[4]: the parameter ensemble, 1024 parameter sets x 100 000 points x 365 days, n_ksub = 3, alb_scheme "none"
+        # (tools.py:31,35); points sharded over the ranks, per-particle sums of squared CRMSDs all-reduced with the LIBRARY's
+        # communicator (run_particles.f90:103-107,165-177 + tools.py:58-62).  The validation series is the model's own daily
+        # output with the default parameters (device resident).
+        try:
+            from semic_b200 import driver
+            rng = np.random.default_rng(SEED)
+            names = ["hcrit", "alb_smax", "amp", "rcrit", "albi", "albl"]                 # optimize/namelist.ranges
+            lo_r = np.array([0.0, 0.80, 0.0, 0.0, 0.35, 0.05]); hi_r = np.array([0.5, 0.9, 5.0, 1.0, 0.55, 0.40])
+            P, NX = 1024, 100000
+            u = (np.stack([rng.permutation(P) for _ in range(6)], axis=1) + rng.uniform(size=(P, 6))) / P
+            pars = driver.particle_params(names, [{"id": i, "pos": list(lo_r + (hi_r - lo_r) * u[i])} for i in range(P)])
+            par3 = make_par(3, args.scheme)
+            lo5, hi5 = driver.shard_bounds(NX, world, rank)
+            n5 = hi5 - lo5
+
+            def ens_inputs(n, p0_):
+                st_o = make_state(n, p0_, 0.85, 0.10)
+                f_ = engine.Series(n, 9, 365).synth_forcing(SEED, point0=p0_)
+                o_ = engine.Series(n, 8, 365)
+                engine.run(st_o, par3, bnd, f_, 365, out=o_, out_days=365)                 # "observations"
+                sp.surface_dealloc(st_o)
+                return make_state(n, p0_, 0.85, 0.10), f_, o_
+
+            st5, f5, o5 = ens_inputs(n5, lo5)
+            comm = None
+            if world > 1:
+                import torch
+                uid = C.create_string_buffer(128)
+                if rank == 0:
+                    check(L.semic_comm_unique_id(uid))
+                t = torch.tensor(list(uid.raw), dtype=torch.uint8, device="cuda")
+                dist.broadcast(t, 0)
+                uid = C.create_string_buffer(bytes(t.cpu().tolist()), 128)
+                comm = C.c_void_p()
+                check(L.semic_comm_init(C.byref(comm), uid, world, rank))
+            engine.ensemble_cost(st5, pars[:8], bnd, f5, o5, 365, 1, comm=comm)
+            best, best_ar, sumsq = None, None, None
+            for _ in range(2):
+                barrier()
+                sumsq, kms = engine.ensemble_cost(st5, pars, bnd, f5, o5, 365, 1, comm=comm)
+                ar = C.c_float(0.0)
+                if comm is not None:
+                    check(L.semic_comm_last_allreduce_ms(comm, C.byref(ar)))
+                tot = maxr([kms + ar.value])[0]
+                kmax = maxr([kms])[0]
+                armin = minr([ar.value])[0]
+                if best is None or tot < best:
+                    best, best_ar, best_k = tot, armin, kmax
+            extra["C5_ensemble_1024x100k_trajectory_days_per_s"] = float(P) * NX * 365 / (best * 1e-3)
+            extra["C5_ms"] = best
+            extra["C5_kernel_ms_max_over_ranks"] = best_k
+            extra["C5_allreduce_ms"] = best_ar
+            extra["C5_note"] = ("points sharded over %d rank(s); kernel + all-reduce device time, max over ranks; all-reduce = ncclAllReduce(sum, 1024 f64) "
+                                "through semic_comm (the fastest rank's figure: the others include waiting for the slowest kernel)" % world)
+            if world > 1:
+                # in-run check: the reduced sums equal a single-GPU evaluation of the WHOLE grid (first 16 particles)
+                if rank == 0:
+                    stf, ff, of_ = ens_inputs(NX, 0)
+                    full, _ = engine.ensemble_cost(stf, pars[:16], bnd, ff, of_, 365, 1)
+                    err = float(np.max(np.abs(sumsq[:16] - full) / np.abs(full)))
+                    extra["C5_allreduce_check_max_rel_err_16_particles"] = err
+                    extra["C5_allreduce_check"] = "ok" if err <= 1e-12 else "FAILED: multi-rank sums differ from the single-GPU evaluation"
+                    for x in (ff, of_):
+                        x.free()
+                    sp.surface_dealloc(stf)
+                check(L.semic_comm_free(comm))
+            for x in (f5, o5):
+                x.free()
+            sp.surface_dealloc(st5)
+        except Exception as e:                                                            # never lose the headline line
+            extra["C5_error"] = str(e)[:200]
+        barrier()
+
+    if rank != 0:
+        if dist is not None:
+            dist.destroy_process_group()
+        return 0
+
+    # ---- rank 0 only: the remaining configurations ----
+    if not args.no_extra:
+        par24 = make_par(24, args.scheme)
         # C4 (configs[3]): isba with surface_boundary_define overrides from an external series, 4 194 304 points, n_ksub=3
         try:
             n4 = 1 << 22
@@ -508,24 +659,9 @@ def main():
         par3 = make_par(3, args.scheme)
         ts = [engine.run(st2, par3, bnd, f2, 365, out=o2, out_days=365) for _ in range(5)]
         extra["C2_100k_points_n_ksub3_point_days_per_s"] = 100000.0 * 365 / (min(ts) * 1e-3)
-        # C5: parameter ensemble, 1024 parameter sets x 100k points x 365 days, n_ksub=3, alb_scheme "none" (tools.py:31,35);
-        # validation series = the model's own daily output with the default parameters (device resident, no host leg)
-        try:
-            from semic_b200 import driver
-            rng = np.random.default_rng(SEED)
-            names = ["hcrit", "alb_smax", "amp", "rcrit", "albi", "albl"]                 # optimize/namelist.ranges
-            lo_r = np.array([0.0, 0.80, 0.0, 0.0, 0.35, 0.05]); hi_r = np.array([0.5, 0.9, 5.0, 1.0, 0.55, 0.40])
-            P = 1024
-            u = (np.stack([rng.permutation(P) for _ in range(6)], axis=1) + rng.uniform(size=(P, 6))) / P
-            pars = driver.particle_params(names, [{"id": i, "pos": list(lo_r + (hi_r - lo_r) * u[i])} for i in range(P)])
-            st5 = make_state(100000, 0, 0.85, 0.10)
-            engine.run(st2, par3, bnd, f2, 365, out=o2, out_days=365)                     # o2: "observations"
-            engine.ensemble_cost(st5, pars[:8], bnd, f2, o2, 365, 1)
-            ms5 = min(engine.ensemble_cost(st5, pars, bnd, f2, o2, 365, 1)[1] for _ in range(2))
-            extra["C5_ensemble_1024x100k_trajectory_days_per_s"] = 1024 * 100000.0 * 365 / (ms5 * 1e-3)
-            extra["C5_ms"] = ms5
-        except Exception as e:                                                            # never lose the headline line
-            extra["C5_error"] = str(e)[:200]
+        for x in (f2, o2):
+            x.free()
+        sp.surface_dealloc(st2)
         line["extra"] = extra
 
     if not args.no_cpu:
@@ -540,6 +676,9 @@ def main():
     _emit(json.dumps(line))
     if dist is not None:
         dist.destroy_process_group()
+    if str(extra.get("C5_allreduce_check", "ok")).startswith("FAILED"):                   # the in-run assertion of the one collective
+        sys.stderr.write("bench.py: %s\n" % extra["C5_allreduce_check"])
+        return 3
     return 0
 
 

@@ -53,6 +53,8 @@ def lib():
         L.oracle_run.argtypes = [dp, C.c_int, ip, C.c_int, C.POINTER(OraclePar), C.POINTER(OracleBnd),
                                  dp, dp, C.c_int, C.c_int, C.c_int, dp, C.c_int, C.c_int, C.c_int, bp]
         L.oracle_run.restype = None
+        L.oracle_run_diag.argtypes = L.oracle_run.argtypes + [dp]
+        L.oracle_run_diag.restype = None
         for name, nargs in [("oracle_sensible_heat_flux", 6), ("oracle_longwave_upward", 2),
                             ("oracle_ew_sat", 1), ("oracle_ei_sat", 1), ("oracle_albedo_slater", 5),
                             ("oracle_albedo_denby", 4)]:
@@ -119,8 +121,9 @@ def step(slab, mask, par, bnd, branch=None):
                       branch.ctypes.data_as(C.POINTER(C.c_ubyte)) if branch is not None else None)
 
 
-def run(slab, mask, par, bnd, forcing, ndays, vali=None, out_days=0, nout=None, want_branch=False, nx=None):
-    """forcing [nwin][9][ldf], vali [nwin][8][ldf] or None.  Returns (out [nout][8][nx] or None, branch or None)."""
+def run(slab, mask, par, bnd, forcing, ndays, vali=None, out_days=0, nout=None, want_branch=False, nx=None, rdiag=None):
+    """forcing [nwin][9][ldf], vali [nwin][8][ldf] or None.  Returns (out [nout][8][nx] or None, branch or None).
+    rdiag: optional float64 [ndays][nx] that receives tmean/amp of every point-day (conditioning report)."""
     nx = slab.shape[1] if nx is None else nx
     nwin, nine, ldf = forcing.shape
     assert nine == 9 and forcing.flags.c_contiguous and forcing.dtype == np.float64
@@ -131,10 +134,12 @@ def run(slab, mask, par, bnd, forcing, ndays, vali=None, out_days=0, nout=None, 
         nout = out_days if nout is None else nout
         out = np.zeros((nout, 8, nx), dtype=np.float64)
     branch = np.zeros((ndays, nx), dtype=np.uint8) if want_branch else None
-    lib().oracle_run(_dp(slab), slab.shape[1], mask.ctypes.data_as(C.POINTER(C.c_int)), nx,
-                     C.byref(par), C.byref(bnd), _dp(forcing), _dp(vali), nwin, ldf, ndays,
-                     _dp(out), (nout or 1), nx, out_days,
-                     branch.ctypes.data_as(C.POINTER(C.c_ubyte)) if branch is not None else None)
+    if rdiag is not None:
+        assert rdiag.shape == (ndays, nx) and rdiag.dtype == np.float64 and rdiag.flags.c_contiguous
+    lib().oracle_run_diag(_dp(slab), slab.shape[1], mask.ctypes.data_as(C.POINTER(C.c_int)), nx,
+                          C.byref(par), C.byref(bnd), _dp(forcing), _dp(vali), nwin, ldf, ndays,
+                          _dp(out), (nout or 1), nx, out_days,
+                          branch.ctypes.data_as(C.POINTER(C.c_ubyte)) if branch is not None else None, _dp(rdiag))
     return out, branch
 
 

@@ -239,6 +239,12 @@ void oracle_mass_balance(oracle_state *now, const oracle_par *par, const oracle_
     }
     for (i = 0; i < nx; ++i)                                                       /* :249 */
         oracle_diurnal_cycle(amp[i], tsurf[i] - t0 + qmr[i] / par->ceff * par->tstic, &above[i], &below[i]);
+    if (now->rdiag) {
+        /* conditioning report: r = tmean/amp of the diurnal cycle (:454).  For |r| -> 1 inside the interior branch the
+         * numerators of :467/:469 cancel to O((1-|r|)^1.5): the reference's own result carries rounding noise of relative
+         * size ~1e-15/(1-|r|)^1.5 there */
+        for (i = 0; i < nx; ++i) now->rdiag[i] = (tsurf[i] - t0 + qmr[i] / par->ceff * par->tstic) / amp[i];
+    }
     if (now->branch) {
         for (i = 0; i < nx; ++i) {
             double tmean = tsurf[i] - t0 + qmr[i] / par->ceff * par->tstic;
@@ -383,7 +389,7 @@ void oracle_step(double *slab, int ld, int *mask, int nx, const oracle_par *par,
                  const oracle_bnd *bnd, unsigned char *branch)
 {
     oracle_state now;
-    now.nx = nx; now.ld = ld; now.slab = slab; now.mask = mask; now.branch = branch;
+    now.nx = nx; now.ld = ld; now.slab = slab; now.mask = mask; now.branch = branch; now.rdiag = NULL;
     if (branch) memset(branch, 0, (size_t)nx);
     oracle_surface_energy_and_mass_balance(&now, par, bnd, 1, 0);
 }
@@ -393,9 +399,16 @@ void oracle_run(double *slab, int ld, int *mask, int nx, const oracle_par *par, 
                 const double *forcing, const double *vali, int nwin, int ldf,
                 int ndays, double *out, int nout, int ldo, int out_days, unsigned char *branch)
 {
+    oracle_run_diag(slab, ld, mask, nx, par, bnd, forcing, vali, nwin, ldf, ndays, out, nout, ldo, out_days, branch, NULL);
+}
+
+void oracle_run_diag(double *slab, int ld, int *mask, int nx, const oracle_par *par, const oracle_bnd *bnd,
+                     const double *forcing, const double *vali, int nwin, int ldf,
+                     int ndays, double *out, int nout, int ldo, int out_days, unsigned char *branch, double *rdiag)
+{
     oracle_state now;
     int d, i;
-    now.nx = nx; now.ld = ld; now.slab = slab; now.mask = mask; now.branch = NULL;
+    now.nx = nx; now.ld = ld; now.slab = slab; now.mask = mask; now.branch = NULL; now.rdiag = NULL;
     for (d = 0; d < ndays; ++d) {
         const double *fr = forcing + (size_t)(d % nwin) * 9u * (size_t)ldf;
         const double *vr = vali ? vali + (size_t)(d % nwin) * 8u * (size_t)ldf : NULL;
@@ -420,6 +433,7 @@ void oracle_run(double *slab, int ld, int *mask, int nx, const oracle_par *par, 
             now.branch = branch + (size_t)d * (size_t)nx;
             memset(now.branch, 0, (size_t)nx);
         }
+        if (rdiag) now.rdiag = rdiag + (size_t)d * (size_t)nx;
         oracle_surface_energy_and_mass_balance(&now, par, bnd, d % nwin + 1, 0);   /* example.f90:112 */
         if (out && d >= ndays - out_days) {                                        /* example.f90:117-122 */
             double *o = out + (size_t)((d - (ndays - out_days)) % nout) * 8u * (size_t)ldo;

@@ -59,6 +59,7 @@ typedef struct oracle_state {
     double *slab;
     int    *mask;
     unsigned char *branch;   /* optional [nx] per-day branch bitmap, NULL = off */
+    double *rdiag;           /* optional [nx] per-day tmean/amp of the diurnal cycle (conditioning report), NULL = off */
 } oracle_state;
 
 /* branch bitmap bits (threshold decisions of one day, used for the flip report) */
@@ -109,6 +110,11 @@ void oracle_step(double *slab, int ld, int *mask, int nx, const oracle_par *par,
 void oracle_run(double *slab, int ld, int *mask, int nx, const oracle_par *par, const oracle_bnd *bnd,
                 const double *forcing, const double *vali, int nwin, int ldf,
                 int ndays, double *out, int nout, int ldo, int out_days, unsigned char *branch);
+
+/* the same, plus rdiag [ndays][nx] (or NULL): r = tmean/amp of every point-day, for the conditioning report */
+void oracle_run_diag(double *slab, int ld, int *mask, int nx, const oracle_par *par, const oracle_bnd *bnd,
+                     const double *forcing, const double *vali, int nwin, int ldf,
+                     int ndays, double *out, int nout, int ldo, int out_days, unsigned char *branch, double *rdiag);
 
 /* surface_physics.f90:601-629; step: 0 "init", 1 "step", 2 "end"; returns -1 for anything else */
 int oracle_field_average(double *ave, const double *now, int nx, int step, double nt);

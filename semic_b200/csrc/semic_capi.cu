@@ -99,6 +99,8 @@ static DevPar make_devpar(const semic_par *par)
     P.inv_mcrit = 1.0 / par->mcrit;
     P.isba_new = par->tstic / P.isba_wcr * P.smax_m_smin;
     P.frz_rhow_clm = P.one_m_frz * rhow * clm;
+    P.inv_tsticsub = 1.0 / par->tsticsub;
+    P.inv_ceff = 1.0 / par->ceff;
     P.n_ksub = par->n_ksub;
     P.scheme = scheme_id(par);
     return P;
@@ -137,6 +139,8 @@ struct semic_series {
 struct semic_comm {
     ncclComm_t comm = nullptr;
     cudaStream_t stream = nullptr;
+    cudaEvent_t e0 = nullptr, e1 = nullptr;      // around the last all-reduce, on `stream`
+    float last_ms = 0.f;
     int nranks = 1, rank = 0;
 };
 
@@ -1187,20 +1191,34 @@ extern "C" int semic_comm_init(semic_comm **out, const char id[128], int nranks,
     if (r != ncclSuccess) { delete c; return nccl_fail(r, "ncclCommInitRank"); }
     cudaError_t e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking);
     if (e != cudaSuccess) { g_nccl.CommDestroy(c->comm); delete c; return cuda_fail(e, "comm_init: stream"); }
+    if ((e = cudaEventCreate(&c->e0)) != cudaSuccess || (e = cudaEventCreate(&c->e1)) != cudaSuccess) {
+        g_nccl.CommDestroy(c->comm); cudaStreamDestroy(c->stream); delete c; return cuda_fail(e, "comm_init: events");
+    }
     *out = c;
     return SEMIC_OK;
 }
 extern "C" int semic_comm_allreduce_sum(semic_comm *c, double *dev_buf, int count)
 {
     if (!c || !dev_buf || count < 0) { set_error("comm_allreduce_sum: bad arguments"); return SEMIC_ERR_ARG; }
+    CU(cudaEventRecord(c->e0, c->stream));
     ncclResult_t r = g_nccl.AllReduce(dev_buf, dev_buf, (size_t)count, ncclFloat64, ncclSum, c->comm, c->stream);
     if (r != ncclSuccess) return nccl_fail(r, "ncclAllReduce");
+    CU(cudaEventRecord(c->e1, c->stream));
     CU(cudaStreamSynchronize(c->stream));
+    CU(cudaEventElapsedTime(&c->last_ms, c->e0, c->e1));
+    return SEMIC_OK;
+}
+extern "C" int semic_comm_last_allreduce_ms(const semic_comm *c, float *ms)
+{
+    if (!c || !ms) { set_error("comm_last_allreduce_ms: bad arguments"); return SEMIC_ERR_ARG; }
+    *ms = c->last_ms;
     return SEMIC_OK;
 }
 extern "C" int semic_comm_free(semic_comm *c)
 {
     if (!c) { set_error("comm_free: null"); return SEMIC_ERR_ARG; }
+    if (c->e0) cudaEventDestroy(c->e0);
+    if (c->e1) cudaEventDestroy(c->e1);
     if (c->stream) cudaStreamDestroy(c->stream);
     if (c->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(c->comm);
     delete c;

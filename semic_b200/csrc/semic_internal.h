@@ -50,6 +50,8 @@ struct DevPar {
     double inv_mcrit;        // 1/mcrit
     double isba_new;         // tstic/(w_crn/rhow)*(alb_smax-alb_smin)
     double frz_rhow_clm;     // (1-f_rz)*rhow*clm
+    double inv_tsticsub;     // 1/tsticsub, 1/ceff: correctly rounded reciprocals for the exact quotients of :202, :249
+    double inv_ceff;
     int    n_ksub;
     int    scheme;
 };

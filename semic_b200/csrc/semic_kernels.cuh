@@ -102,6 +102,13 @@ DEVI double frcp(double d)
     return fma(r, t, r);
 }
 DEVI double fdiv(double n, double d) { return n * frcp(d); }
+// n/d correctly rounded from the correctly rounded reciprocal rd = RN(1/d) (Markstein): q0 = RN(n*rd),
+// q = RN(q0 + RN(n - q0*d)*rd); 3 FP64 operations, no special cases (finite, normal operands)
+DEVI double fdiv_rn(double n, double d, double rd)
+{
+    const double q0 = n * rd;
+    return fma(fma(-q0, d, n), rd, q0);
+}
 // exp for |x| < 700 without special-case handling: Cody-Waite reduction by ln2 and the
 // degree-11 minimax polynomial (max rel. error 4e-18 before rounding).
 DEVI double fexp(double x)
@@ -551,7 +558,11 @@ DEVI unsigned point_day(Pt &s, const double *row, const long long T, const DevPa
 #if SEMIC_STRICT
             qmr = fdiv(over * P.ceff, P.tsticsub);                                 // :202 (0 when the clamp did not fire)
 #else
-            qmr = over * P.ceff_over_sub;
+            // :202 in the reference's own rounding sequence ((ts-t0)*ceff, then the IEEE quotient): the diurnal cycle below
+            // amplifies the last bit of tmean by up to 1e5 (see diurnal_cycle_fast), so qmr and tmean are reproduced exactly
+            // whenever the clamp excess itself is; days without a clamped lane (3 of 4) skip it
+            qmr = 0.0;
+            if (__any_sync(__activemask(), over > 0.0)) qmr = fdiv_rn(__dmul_rn(over, P.ceff), P.tsticsub, P.inv_tsticsub);
 #endif
             if (WANT_BRANCH) { if (over > 0.0) branch |= SEMIC_B_CLAMP; }
             if (!BND(lhf)) {
@@ -579,7 +590,9 @@ DEVI unsigned point_day(Pt &s, const double *row, const long long T, const DevPa
 #if SEMIC_STRICT
         const double tmean = (ts - c_t0) + (fdiv(qmr, P.ceff) * P.tstic);          // :249
 #else
-        const double tmean = fma(qmr, P.tstic_over_ceff, ts - kc[14]);
+        double tmean = ts - kc[14];                                                // :249, unfused like the reference
+        if (__any_sync(__activemask(), qmr != 0.0))
+            tmean = __dadd_rn(tmean, __dmul_rn(fdiv_rn(qmr, P.ceff, P.inv_ceff), P.tstic));
 #endif
         double above, below;
 #if SEMIC_STRICT

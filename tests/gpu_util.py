@@ -64,10 +64,17 @@ def run_gpu(slab, mask, par_d, bnd_names, forcing, ndays, vali=None, out_days=0,
 
 
 def run_oracle(slab, mask, par_d, bnd_names, forcing, ndays, vali=None, out_days=0):
+    return run_oracle_diag(slab, mask, par_d, bnd_names, forcing, ndays, vali=vali, out_days=out_days)[:3]
+
+
+def run_oracle_diag(slab, mask, par_d, bnd_names, forcing, ndays, vali=None, out_days=0):
+    """-> (final slab, out, branch bitmap, r) with r = tmean/amp of the diurnal cycle per point-day (util.ill_conditioned)"""
     S = slab.copy()
     m = mask.copy()
+    r = np.zeros((ndays, slab.shape[1]))
     out, br = ob.run(S, m, ob.make_par(par_d), ob.make_bnd(bnd_names), forcing, ndays, vali=vali,
-                     out_days=out_days, want_branch=True)
+                     out_days=out_days, want_branch=True, rdiag=r)
     if br is not None and out_days > 0:
         br = br[ndays - out_days:]
-    return S, out, br
+        r = r[ndays - out_days:]
+    return S, out, br, r

@@ -12,22 +12,26 @@ def report(label, par, forc, mask, ndays, strict, vali=None, bnd=()):
     nx = forc.shape[2]
     S0, m0 = util.init_slab(nx, mask)
     fin_g, out_g, br_g, ms = gpu_util.run_gpu(S0, m0, par, bnd, forc, ndays, vali=vali, out_days=ndays, strict=strict)
-    fin_o, out_o, br_o = gpu_util.run_oracle(S0, m0, par, bnd, forc, ndays, vali=vali, out_days=ndays)
+    fin_o, out_o, br_o, r_o = gpu_util.run_oracle_diag(S0, m0, par, bnd, forc, ndays, vali=vali, out_days=ndays)
     diff = br_g ^ br_o
     taint = util.tainted(br_g, br_o)
+    ill = util.ill_conditioned(r_o, br_o) & ~taint
     oe = util.out_errors(out_g, out_o, exclude=taint)
-    oe_all = util.out_errors(out_g, out_o, exclude=taint, pointwise=True)
+    oe_all = util.out_errors(out_g, out_o, exclude=taint | ill, pointwise=True)
+    oe_ill = util.out_errors(out_g, out_o, exclude=~ill, pointwise=True)
     se = util.state_errors(fin_g, fin_o, exclude_points=taint.any(axis=0))
     print("== %s nx=%d days=%d k=%d scheme=%s strict=%d  kernel %.2f ms" % (label, nx, ndays, par["n_ksub"], par["alb_scheme"], strict, ms))
     print("   daily field-relative (untainted):", " ".join("%s=%.1e" % kv for kv in oe.items()))
-    print("   daily pointwise+floor (untainted):", " ".join("%s=%.1e" % kv for kv in oe_all.items()))
+    print("   daily pointwise+floor (untainted, well-conditioned):", " ".join("%s=%.1e" % kv for kv in oe_all.items()))
+    print("   ill-conditioned point-days (diurnal interior, 1-|tmean/amp| < %.0e): %d of %d (%.4f%%); pointwise+floor on them: %s"
+          % (util.ILL_MARGIN, int(ill.sum()), ill.size, 100.0 * ill.mean(), " ".join("%s=%.1e" % kv for kv in oe_ill.items())))
     print("   tainted point-days: %d of %d (%.4f%%) on %d points" % (int(taint.sum()), taint.size, 100.0 * taint.mean(), int(taint.any(axis=0).sum())))
     print("   final state worst: %s" % ", ".join("%s=%.1e" % (k, v) for k, v in sorted(se.items(), key=lambda kv: -kv[1])[:5]))
     print("   flips: %d point-days on %d points; by bit: %s" % (int((diff != 0).sum()), int((diff != 0).any(axis=0).sum()),
           " ".join("%s=%d" % (BITS[b], int(((diff >> b) & 1).sum())) for b in range(8))))
     for v in (3, 4, 5, 6):
         e = util.rel_err(out_g[:, v, :], out_o[:, v, :], util.OUT_FLOOR[v])
-        e = np.where(taint, 0.0, e)
+        e = np.where(taint | ill, 0.0, e)
         d, i = np.unravel_index(np.argmax(e), e.shape)
         print("   worst %s: day %d pt %d mask %d gpu=%.17g ref=%.17g rel=%.2e | bits=%s | stt=%.17g/%.17g t2m=%.6f swd=%.3f sf=%.3e rf=%.3e prev-day stt diff=%.2e"
               % (util.OUT_NAMES[v], d, i, mask[i], out_g[d, v, i], out_o[d, v, i], e[d, i], bin(br_o[d, i]), out_g[d, 0, i], out_o[d, 0, i],

@@ -59,15 +59,16 @@ def test_oracle_reproduces_the_reference_golden_vectors(name, scheme, k, nloop):
     assert np.array_equal(out.view(np.uint64), gold.view(np.uint64))
 
 
-def test_oracle_reproduces_the_reference_particle_costs():
+@pytest.mark.parametrize("label,mask", [("", [1, 1, 1, 2, 2, 2, 2]), ("_ice", [2] * 7)])
+def test_oracle_reproduces_the_reference_particle_costs(label, mask):
     """ref_particles_cost.npy: optimize/run_particles.f90 (translated) on the shipped optimization.namelist, three
     particles in one process: state carried over from particle to particle (Q14), nloop = 20"""
     import json
-    gold = np.load(os.path.join(util.GOLDEN, "ref_particles_cost.npy"))
+    gold = np.load(os.path.join(util.GOLDEN, "ref_particles_cost%s.npy" % label))
     pars = json.load(open(os.path.join(util.GOLDEN, "ref_particles_pars.json")))
     forc, vali = util.load_fixture("transect")
     S, m = ob.new_state(7)
-    m[:] = [1, 1, 1, 2, 2, 2, 2]                                               # optimization.namelist:5
+    m[:] = mask                                                                # optimization.namelist:5 / all ice
     S[ob.FIDX["hsnow"]] = 1.0                                                  # run_particles.f90:77-82
     S[ob.FIDX["alb"]] = vali[0, 1]
     S[ob.FIDX["tsurf"]] = vali[0, 0]
