@@ -31,9 +31,16 @@ class OracleBnd(C.Structure):
     _fields_ = [(n, C.c_int) for n in BND_NAMES]
 
 
+class OracleState(C.Structure):
+    """oracle_state of semic_oracle.h (for tests that call oracle_energy_balance / oracle_mass_balance directly)"""
+    _fields_ = [("nx", C.c_int), ("ld", C.c_int), ("slab", C.POINTER(C.c_double)), ("mask", C.POINTER(C.c_int)),
+                ("branch", C.POINTER(C.c_ubyte)), ("rdiag", C.POINTER(C.c_double))]
+
+
 def build(force=False):
     src = os.path.join(_HERE, "semic_oracle.c")
-    if force or not os.path.exists(_SO) or os.path.getmtime(_SO) < os.path.getmtime(src):
+    hdr = os.path.join(_HERE, "semic_oracle.h")
+    if force or not os.path.exists(_SO) or os.path.getmtime(_SO) < max(os.path.getmtime(src), os.path.getmtime(hdr)):
         subprocess.check_call(["make", "-C", _HERE, "-s", "libsemic_oracle.so"])
     return _SO
 

@@ -564,10 +564,8 @@ def test_energy_and_mass_balance_separately():
     import oracle.binding as b
     L = b.lib()
 
-    class OS(C.Structure):
-        _fields_ = [("nx", C.c_int), ("ld", C.c_int), ("slab", C.POINTER(C.c_double)), ("mask", C.POINTER(C.c_int)),
-                    ("branch", C.POINTER(C.c_ubyte))]
-    os_ = OS(7, 7, S.ctypes.data_as(C.POINTER(C.c_double)), m0.ctypes.data_as(C.POINTER(C.c_int)), None)
+    OS = b.OracleState
+    os_ = OS(7, 7, S.ctypes.data_as(C.POINTER(C.c_double)), m0.ctypes.data_as(C.POINTER(C.c_int)), None, None)
     L.oracle_energy_balance.argtypes = [C.POINTER(OS), C.POINTER(b.OraclePar), C.POINTER(b.OracleBnd)]
     L.oracle_mass_balance.argtypes = [C.POINTER(OS), C.POINTER(b.OraclePar), C.POINTER(b.OracleBnd)]
     for it in range(4):
