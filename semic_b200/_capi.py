@@ -7,7 +7,8 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libsemic_b200.so")
+# SEMIC_B200_LIB: another build of the same library (A/B timing of two builds on one box, tools/ab_builds.sh); never a fallback
+LIB_PATH = os.environ.get("SEMIC_B200_LIB") or os.path.join(_HERE, "lib", "libsemic_b200.so")
 
 STRLEN = 256
 NBOUNDARY = 30

@@ -241,6 +241,49 @@ DEVI double latent_q(double ts, double A, double Bq, double sp, bool ice, const 
     const double em = fexp_t((na * x) * frcp(b + x), tab);
     return fma(frcp(fma(sp, em, kc[16])), A, -Bq);
 }
+// warm = (raw >= t0) as ONE signed 64-bit compare of the bit patterns, feeding both selects: tsurf of the next sub-step
+// (clamped at t0 when gated) and the latent heat it will use.  Written in PTX so that the two selects share the predicate
+// (left to itself the compiler turns the first into an integer minimum and re-issues the compare for the second).
+DEVI void clamp_and_latent(const double raw, const long long t0_bits, const double t0, const bool gate, const double cls_,
+                           const double clv_, double &ts, double &lat)
+{
+    asm("{\n"
+        ".reg .pred p, g, c;\n"
+        "setp.ge.s64 p, %2, %3;\n"
+        "setp.ne.u32 g, %4, 0;\n"
+        "and.pred c, p, g;\n"
+        "selp.f64 %0, %5, %6, c;\n"
+        "selp.f64 %1, %7, %8, p;\n"
+        "}\n"
+        : "=d"(ts), "=d"(lat)
+        : "l"(__double_as_longlong(raw)), "l"(t0_bits), "r"((unsigned)gate), "d"(t0), "d"(raw), "d"(clv_), "d"(cls_));
+}
+// ... and the pair (-a, b) of ew_sat / ei_sat for a warp that has lanes above the melting point
+DEVI void clamp_and_latent_ab(const double raw, const long long t0_bits, const double t0, const bool gate, const double cls_,
+                              const double clv_, const double nai, const double naw, const double bi, const double bw,
+                              double &ts, double &lat, double &na, double &b)
+{
+    asm("{\n"
+        ".reg .pred p, g, c;\n"
+        "setp.ge.s64 p, %4, %5;\n"
+        "setp.ne.u32 g, %6, 0;\n"
+        "and.pred c, p, g;\n"
+        "selp.f64 %0, %7, %8, c;\n"
+        "selp.f64 %1, %9, %10, p;\n"
+        "selp.f64 %2, %11, %12, p;\n"
+        "selp.f64 %3, %13, %14, p;\n"
+        "}\n"
+        : "=d"(ts), "=d"(lat), "=d"(na), "=d"(b)
+        : "l"(__double_as_longlong(raw)), "l"(t0_bits), "r"((unsigned)gate), "d"(t0), "d"(raw), "d"(clv_), "d"(cls_),
+          "d"(naw), "d"(nai), "d"(bw), "d"(bi));
+}
+// the same with the pair (-a, b) of ei_sat / ew_sat already selected by the caller
+DEVI double latent_q_ab(double ts, double A, double Bq, double sp, double na, double b, const double *tab)
+{
+    const double x = ts - kc[14];
+    const double em = fexp_t((na * x) * frcp(b + x), tab);
+    return fma(frcp(fma(sp, em, kc[16])), A, -Bq);
+}
 #endif
 
 // longwave_upward, surface_physics.f90:434-438
@@ -435,28 +478,36 @@ DEVI void energy_substeps(double &ts, double &t2m, double &shf, double &lhf, dou
     double ts_raw = ts;                                                        // tsurf of the last sub-step before the clamp
     const double lat_a = lhf_c * kc[15], lat_b = lhf_c * qq;                   // day constants of latent_q
     const double radq = rad - qmr_res;                                         // :194 with the day-constant terms first
+    // per-lane constant that replaces a select inside the loop: an ungated lane adds (shf+lhf)*0 to t2m
+    const double cg = gate ? c : 0.0;                                          // :209-211 as t2m += (shf+lhf)*cg
+    const long long t0_bits = __double_as_longlong(t0);
     if (!GENERIC) {
         // the diagnostics shf, lhf, lwu of the last sub-step are formed after the loop from d, q, latent heat and ts^4
         double d = 0.0, q = 0.0, lat = 0.0, t4 = 0.0;
-        bool ice = false;
-        // ts < t0 and ts_raw > t0 as signed 64-bit integer compares of the bit patterns: identical to the floating-point
+        // ts < t0 as a signed 64-bit integer compare of the bit patterns: identical to the floating-point
         // compares for every non-NaN ts (t0 > 0), and they run on the ALU pipe in the shadow of the FP64 pipe, which is the
-        // busy one (DSETP costs it two cycles per warp, profiles/r01_summary.md section 4)
-        const long long t0_bits = __double_as_longlong(t0);
+        // busy one (DSETP costs it two cycles per warp, profiles/r01_summary.md section 4).  One compare per sub-step serves
+        // both decisions: the next sub-step's ts < t0 (:415) is !(ts_raw >= t0) whether or not the clamp fires.
+        // The selects that depend on it (latent heat, the ei/ew constants) are made right at the compare, for the NEXT sub-step,
+        // and carried as values: the compiler otherwise re-issues the compare at every use.
+        const bool ice0 = __double_as_longlong(ts) < t0_bits;
+        double lat_next = ice0 ? kc[22] : kc[23];
+        double na = (ALLG || ice0) ? kc[24] : kc[25], b = (ALLG || ice0) ? kc[19] : kc[21];
 #pragma unroll UNR
         for (int k = 0; k < nsub; ++k) {
-            ice = __double_as_longlong(ts) < t0_bits;                          // :415
-            q = latent_q<ALLG>(ts, lat_a, lat_b, sp, ice, tab);                // :179-185
-            lat = ice ? kc[22] : kc[23];
+            lat = lat_next;                                                    // :415 decided on the tsurf this sub-step starts from
+            q = latent_q_ab(ts, lat_a, lat_b, sp, na, b, tab);                 // :179-185
             d = ts - t2m;                                                      // :173
             const double t2 = ts * ts;
             t4 = t2 * t2;                                                      // :191
-            const double lh = lat * q;
-            const double qsb = fma(-shf_c, d, fma(-sigm, t4, radq)) - lh;      // :194
-            if (gate) t2m = fma(fma(shf_c, d, lh), c, t2m);                    // :209-211 (Q1: forcing t2m is mutated)
+            const double sl = fma(shf_c, d, lat * q);                          // shf + lhf, shared by :194 and :210
+            const double qsb = fma(-sigm, t4, radq) - sl;                      // :194
+            t2m = fma(sl, cg, t2m);                                            // :209-211 (Q1: forcing t2m is mutated)
             if (!BNDX(tsurf)) {                                                // :198 (external tsurf stays as given)
                 ts_raw = fma(qsb, c, ts);                                      // :199
-                ts = (gate && __double_as_longlong(ts_raw) > t0_bits) ? t0 : ts_raw;   // :201-204; the excess is formed below
+                // warm = !(tsurf < t0) of the next sub-step; tsurf = t0 if gated and warm (:201-204; ts_raw == t0: the same value)
+                if (ALLG) clamp_and_latent(ts_raw, t0_bits, t0, gate, kc[22], kc[23], ts, lat_next);
+                else      clamp_and_latent_ab(ts_raw, t0_bits, t0, gate, kc[22], kc[23], kc[24], kc[25], kc[19], kc[21], ts, lat_next, na, b);
             }
         }
         if (nsub > 0) {
@@ -464,7 +515,7 @@ DEVI void energy_substeps(double &ts, double &t2m, double &shf, double &lhf, dou
             lhf = lat * q;
             lwu = sigm * t4;
             q_last = q;
-            ice_last = ice;
+            ice_last = __double2hiint(lat) == __double2hiint(kc[22]);          // the latent heat in use was cls (:421)
         }
     } else {
         // all boundary flags; the same fused forms as above wherever the flag set allows, so that a run whose flags are
@@ -486,17 +537,16 @@ DEVI void energy_substeps(double &ts, double &t2m, double &shf, double &lhf, dou
             const double t2 = ts * ts;
             const double t4 = t2 * t2;
             lwu = sigm * t4;                                                   // :191
-            double qsb, sl;
+            double sl;
             if (!BND(shf)) {
                 const double d = ts - t2m;                                     // :173
                 shf = shf_c * d;
-                qsb = fma(-shf_c, d, fma(-sigm, t4, radq)) - lh;               // :194
                 sl = fma(shf_c, d, lh);
             } else {
-                qsb = (fma(-sigm, t4, radq) - shf) - lh;
                 sl = shf + lh;
             }
-            if (gate) t2m = fma(sl, c, t2m);                                   // :209-211
+            const double qsb = fma(-sigm, t4, radq) - sl;                      // :194
+            t2m = fma(sl, cg, t2m);                                            // :209-211
             if (!BNDX(tsurf)) {                                                // :198-204
                 ts_raw = fma(qsb, c, ts);
                 ts = (gate && ts_raw > t0) ? t0 : ts_raw;

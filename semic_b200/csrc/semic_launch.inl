@@ -90,6 +90,7 @@ static cudaError_t launch_lean(const RunArgs &a, cudaStream_t st, int ext)
         return launch_lean_nk<20, 2, 0, true>(a, st);
     }
     if (a.P.n_ksub == 3) return launch_lean_nk<24, 3, 3, false>(a, st);
+    if (a.P.n_ksub == 24) return launch_lean_nk<24, 4, 24, false>(a, st);     // BASELINE configs[1]: trip count known, unrolled by 4
     if (a.P.n_ksub >= 8) return launch_lean_nk<24, 4, 0, false>(a, st);
     return launch_lean_nk<24, 2, 0, false>(a, st);
 }
