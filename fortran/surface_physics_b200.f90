@@ -21,6 +21,7 @@
 module surface_physics
 
     use, intrinsic :: iso_c_binding
+    use, intrinsic :: ieee_arithmetic, only: ieee_value, ieee_quiet_nan
     implicit none
 
     integer, parameter:: dp=kind(0.d0)
@@ -166,6 +167,45 @@ module surface_physics
         type(c_ptr) function semic_last_error() bind(C, name="semic_last_error")
             import :: c_ptr
         end function
+        ! the three public elementals, evaluated by the library on the device over n values (include/semic_b200.h).
+        ! Declared PURE (they have no side effect visible to Fortran; the result arrays are reached through C pointers
+        ! passed by value), so that the module can keep the reference's ELEMENTAL interfaces on top of them.
+        pure integer(c_int) function semic_shf_c(ts, ta, wind, rhoa, csh, cap, shf, n) bind(C, name="semic_sensible_heat_flux")
+            import :: c_int, c_double, c_ptr
+            real(c_double), intent(in) :: ts(*), ta(*), wind(*), rhoa(*)
+            real(c_double), value :: csh, cap
+            type(c_ptr), value :: shf
+            integer(c_int), value :: n
+        end function
+        pure integer(c_int) function semic_lhf_c(ts, wind, shum, sp, rhoatm, mask, clh, eps, cls, clv, lhf, subl, evap, n) &
+                bind(C, name="semic_latent_heat_flux")
+            import :: c_int, c_double, c_ptr
+            real(c_double), intent(in) :: ts(*), wind(*), shum(*), sp(*), rhoatm(*)
+            integer(c_int), intent(in) :: mask(*)
+            real(c_double), value :: clh, eps, cls, clv
+            type(c_ptr), value :: lhf, subl, evap
+            integer(c_int), value :: n
+        end function
+        pure integer(c_int) function semic_lwu_c(ts, sigma, lwout, n) bind(C, name="semic_longwave_upward")
+            import :: c_int, c_double, c_ptr
+            real(c_double), intent(in) :: ts(*)
+            real(c_double), value :: sigma
+            type(c_ptr), value :: lwout
+            integer(c_int), value :: n
+        end function
+    end interface
+
+    ! Generic names = the reference's elemental subroutines (surface_physics.f90:378-438).  Both specifics forward to the
+    ! C-ABI: the rank-1 specific in ONE call over the whole array (it takes precedence over the elemental one when the
+    ! actual arguments are rank-1 arrays, as in energy_balance :173, :183, :191), the elemental one value by value.
+    interface sensible_heat_flux
+        module procedure sensible_heat_flux_v, sensible_heat_flux_e
+    end interface
+    interface latent_heat_flux
+        module procedure latent_heat_flux_v, latent_heat_flux_e
+    end interface
+    interface longwave_upward
+        module procedure longwave_upward_v, longwave_upward_e
     end interface
 
     private
@@ -280,36 +320,58 @@ contains
         call check(semic_mass_balance_c(now%handle, pc, bc, int(day, c_int), int(year, c_int)), 'mass_balance')
     end subroutine
 
-    !> elementals keep their reference bodies (they are public in the module and trivially cheap on the host)
-    elemental subroutine sensible_heat_flux(ts, ta, wind, rhoa, csh, cap, shf)
-        double precision, intent(in) :: ts, ta, wind, rhoa, csh, cap
-        double precision, intent(out) :: shf
-        shf = csh*cap*rhoa*wind*(ts-ta)
+    !> surface_physics.f90:378-389, forwarded to the library (no host arithmetic here)
+    subroutine sensible_heat_flux_v(ts, ta, wind, rhoa, csh, cap, shf)
+        double precision, intent(in) :: ts(:), ta(:), wind(:), rhoa(:), csh, cap
+        double precision, intent(out), target, contiguous :: shf(:)
+        call check(semic_shf_c(ts, ta, wind, rhoa, csh, cap, c_loc(shf), int(size(ts), c_int)), 'sensible_heat_flux')
     end subroutine
 
-    elemental subroutine latent_heat_flux(ts, wind, shum, sp, rhoatm, mask, clh, eps, cls, clv, lhf, subl, evap)
+    elemental subroutine sensible_heat_flux_e(ts, ta, wind, rhoa, csh, cap, shf)
+        double precision, intent(in) :: ts, ta, wind, rhoa, csh, cap
+        double precision, intent(out) :: shf
+        real(c_double), target :: o(1)
+        integer(c_int) :: rc
+        rc = semic_shf_c([ts], [ta], [wind], [rhoa], csh, cap, c_loc(o), 1_c_int)
+        shf = merge(o(1), ieee_value(o(1), ieee_quiet_nan), rc == 0)      ! a pure procedure cannot stop: failure -> NaN
+    end subroutine
+
+    !> surface_physics.f90:393-430
+    subroutine latent_heat_flux_v(ts, wind, shum, sp, rhoatm, mask, clh, eps, cls, clv, lhf, subl, evap)
+        double precision, intent(in)  :: ts(:), wind(:), shum(:), sp(:), rhoatm(:), clh, eps, cls, clv
+        integer,          intent(in)  :: mask(:)
+        double precision, intent(out), target, contiguous :: lhf(:), subl(:), evap(:)
+        call check(semic_lhf_c(ts, wind, shum, sp, rhoatm, int(mask, c_int), clh, eps, cls, clv, &
+                               c_loc(lhf), c_loc(subl), c_loc(evap), int(size(ts), c_int)), 'latent_heat_flux')
+    end subroutine
+
+    elemental subroutine latent_heat_flux_e(ts, wind, shum, sp, rhoatm, mask, clh, eps, cls, clv, lhf, subl, evap)
         double precision, intent(in)  :: ts, shum, sp, rhoatm, wind, clh, eps, cls, clv
         integer,          intent(in)  :: mask
         double precision, intent(out) :: lhf, evap, subl
-        double precision :: esat_sur, shum_sat
-        subl = 0.0_dp; evap = 0.0_dp; lhf = 0.0_dp
-        if (ts < t0) then
-            esat_sur = 611.2_dp*dexp(22.46_dp*(ts-t0)/(272.62_dp+ts-t0))
-            shum_sat = esat_sur*eps/(esat_sur*(eps-1.0_dp)+sp)
-            subl = clh*wind*rhoatm*(shum_sat-shum)
-            lhf = subl*cls
-        else
-            esat_sur = 611.2_dp*dexp(17.62_dp*(ts-t0)/(243.12_dp+ts-t0))
-            shum_sat = esat_sur*eps/(esat_sur*(eps-1.0_dp)+sp)
-            evap = clh*wind*rhoatm*(shum_sat-shum)
-            lhf = evap*clv
-        end if
+        real(c_double), target :: o1(1), o2(1), o3(1)
+        integer(c_int) :: rc
+        rc = semic_lhf_c([ts], [wind], [shum], [sp], [rhoatm], [int(mask, c_int)], clh, eps, cls, clv, &
+                         c_loc(o1), c_loc(o2), c_loc(o3), 1_c_int)
+        lhf  = merge(o1(1), ieee_value(o1(1), ieee_quiet_nan), rc == 0)
+        subl = merge(o2(1), ieee_value(o2(1), ieee_quiet_nan), rc == 0)
+        evap = merge(o3(1), ieee_value(o3(1), ieee_quiet_nan), rc == 0)
     end subroutine
 
-    elemental subroutine longwave_upward(ts,sigma,lwout)
+    !> surface_physics.f90:434-438
+    subroutine longwave_upward_v(ts, sigma, lwout)
+        double precision, intent(in) :: ts(:), sigma
+        double precision, intent(out), target, contiguous :: lwout(:)
+        call check(semic_lwu_c(ts, sigma, c_loc(lwout), int(size(ts), c_int)), 'longwave_upward')
+    end subroutine
+
+    elemental subroutine longwave_upward_e(ts, sigma, lwout)
         double precision, intent(in) :: ts, sigma
         double precision, intent(out) :: lwout
-        lwout = sigma*ts*ts*ts*ts
+        real(c_double), target :: o(1)
+        integer(c_int) :: rc
+        rc = semic_lwu_c([ts], sigma, c_loc(o), 1_c_int)
+        lwout = merge(o(1), ieee_value(o(1), ieee_quiet_nan), rc == 0)
     end subroutine
 
     !> surface_physics.f90:565-597 (device side; ave and now must both be allocated with surface_alloc)

@@ -3,12 +3,14 @@
 // Reads &driver from ./optimization.namelist, the forcing/validation tables, then for every particle i in [i0,i1] with
 // a namelist <prefix>NNNNNN.nml writes the cost to <prefix>NNNNNN.out (run_particles.f90:104-178) -- the file protocol
 // of optimize/tools.py:46-63.  All particles of the call are ONE ensemble launch (semic_ensemble_cost); with several
-// GPUs visible the grid points are sharded over them and the per-particle sums are added on the host (the NCCL path
-// of the library is for one process per GPU, see semic_b200/driver.py).
+// GPUs visible the grid points are sharded over them, the shards run CONCURRENTLY (one host thread per device) and the
+// per-particle sums are added on the host in device order (the NCCL path of the library is for one process per GPU,
+// see semic_b200/driver.py and bench.py).
 // Deviation: every particle starts from the same initial state; the reference carries the state of
 // particle i-1 into particle i.
 #include <cmath>
 #include <sys/stat.h>
+#include <thread>
 
 #include "driver_util.h"
 
@@ -58,10 +60,11 @@ int main(int argc, char **argv)
         int ndev = semic_device_count();
         if (ndev < 1) die(std::string("no CUDA device: ") + semic_last_error());
         if (ndev > nx) ndev = nx;
-        std::vector<double> sumsq(pars.size(), 0.0), part(pars.size());
-        for (int dev = 0; dev < ndev; ++dev) {                       // contiguous point shards, one per GPU
+        std::vector<double> sumsq(pars.size(), 0.0);
+        std::vector<std::vector<double>> part(ndev, std::vector<double>(pars.size(), 0.0));
+        auto run_shard = [&](int dev) {                              // contiguous point shard [lo, hi) on GPU `dev`
             const int lo = (int)((long long)nx * dev / ndev), hi = (int)((long long)nx * (dev + 1) / ndev), n = hi - lo;
-            if (n == 0) continue;
+            if (n == 0) return;
             check(semic_set_device(dev), "set_device");
             semic_state *now = nullptr;
             check(semic_surface_alloc(&now, n), "surface_alloc");                                     // :74
@@ -84,12 +87,20 @@ int main(int argc, char **argv)
             check(semic_series_upload(fs, 0, ntime, forc.data() + lo, nx), "series_upload");
             check(semic_series_upload(vs, 0, ntime, vali.data() + lo, nx), "series_upload");
             float ms = 0.f;
-            check(semic_ensemble_cost(now, pars.data(), (int)pars.size(), &bnd, fs, vs, ntime, d.nloop, nullptr, part.data(), &ms),
+            check(semic_ensemble_cost(now, pars.data(), (int)pars.size(), &bnd, fs, vs, ntime, d.nloop, nullptr, part[dev].data(), &ms),
                   "semic_ensemble_cost");                                                             // :124-174
-            for (size_t p = 0; p < pars.size(); ++p) sumsq[p] += part[p];
             semic_series_free(fs); semic_series_free(vs);
             check(semic_surface_dealloc(now), "surface_dealloc");                                     // :181
+        };
+        if (ndev == 1) {
+            run_shard(0);
+        } else {
+            std::vector<std::thread> th;
+            for (int dev = 0; dev < ndev; ++dev) th.emplace_back(run_shard, dev);
+            for (auto &t : th) t.join();
         }
+        for (int dev = 0; dev < ndev; ++dev)                          // fixed order: reproducible sums
+            for (size_t p = 0; p < pars.size(); ++p) sumsq[p] += part[dev][p];
         for (size_t p = 0; p < pars.size(); ++p) {
             std::snprintf(name, sizeof name, "%s%06d.out", prefix.c_str(), ids[p]);                   // :119-120
             std::FILE *f = std::fopen(name, "w");

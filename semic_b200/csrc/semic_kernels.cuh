@@ -663,17 +663,16 @@ DEVI unsigned point_day(Pt &s, const double *row, const long long T, const DevPa
 #endif
         }
 #if !SEMIC_STRICT
-        {   // above >= 0 on return from diurnal_cycle_fast and dmax1(0,|x|) == |x|; finite values times 0 are the :252-261 zeros
-            const double c_mask = (mask >= 1) ? P.ceff_over_tstic : 0.0;
-            qmelt = above * c_mask;
-            qcold = fabs(below) * c_mask;
-        }
+        // above >= 0 on return from diurnal_cycle_fast and dmax1(0,|x|) == |x|; finite values times 0 are the :252-261 zeros.
+        // qmelt and qcold only feed melt (:266) and refr (:286): one multiplication by ceff/tstic/(rhow*clm) each
+        const double c_mask = (mask >= 1) ? P.melt_per_kelvin : 0.0;
+        (void)qmelt; (void)qcold;
 #endif
 #if SEMIC_STRICT
         if (!BND(melt)) melt = fdiv(qmelt, P.rhow_clm);                            // :266
         const double hs_rate = fdiv(hsnow, P.tstic);
 #else
-        if (!BND(melt)) melt = qmelt * P.inv_rhow_clm;
+        if (!BND(melt)) melt = above * c_mask;
         // IEEE quotient: when all snow melts, hsnow - (hsnow/tstic)*tstic decides between "bare" and a
         // one-ulp ghost snow layer (which keeps the :201 gate on over land); keep the reference's rounding
         // (one Newton refinement of hsnow*(1/tstic) is the correctly rounded quotient up to ~2^-50 odds: 3 instructions
@@ -693,7 +692,7 @@ DEVI unsigned point_day(Pt &s, const double *row, const long long T, const DevPa
 #if SEMIC_STRICT
             refr = fdiv(qcold, P.rhow_clm);                                        // :286
 #else
-            refr = qcold * P.inv_rhow_clm;
+            refr = fabs(below) * c_mask;
 #endif
             refrozen_rain = dmin1(refr, rf);                                        // :287
 #if SEMIC_STRICT
@@ -771,9 +770,11 @@ DEVI unsigned point_day(Pt &s, const double *row, const long long T, const DevPa
                 alb = alb_snow;
             }
 #else
-            if (mask == 2)      alb = fma(f_alb, alb_snow - P.albi, P.albi);
-            else if (mask == 1) alb = fma(f_alb, alb_snow - P.albl, P.albl);
-            else if (mask == 0) alb = 0.06;
+            {   // :350-358 with the background albedo selected first (a per-lane constant): one blend instead of two
+                const double bg = (mask == 2) ? P.albi : P.albl;
+                const double blend = fma(f_alb, alb_snow - bg, bg);
+                alb = (mask == 1 || mask == 2) ? blend : ((mask == 0) ? 0.06 : alb);     // Q7: other masks leave alb unchanged
+            }
             if (scheme == SCHEME_ALEX) {
                 alb_snow = fma(P.smax_m_smin, fma(0.5, tanh(P.afac * (t2m - P.tmid)), 0.5), P.alb_smin);
                 alb = alb_snow;
@@ -1074,7 +1075,7 @@ DEVI bool elect_one()
 template <int WPC, int EXT>
 struct LeanSmem {
     static constexpr int ROWS = kForcingRows + (EXT == 2 ? 6 : (EXT == 1 ? 2 : 0));
-    static constexpr int STAGES = kStages;
+    static constexpr int STAGES = (WPC > 24) ? 2 : kStages;                                  // 227 KB of shared memory per CTA
     static constexpr size_t stage_bytes = (size_t)ROWS * kTile * sizeof(double);           // 2304 B (2816 / 3840 B with external rows)
     static constexpr size_t ring_bytes = stage_bytes * STAGES * WPC;
     static constexpr size_t bar_bytes = (size_t)WPC * STAGES * sizeof(uint64_t);
@@ -1273,6 +1274,7 @@ __global__ void __launch_bounds__(WPC * 32, 1) k_run_lean(const __grid_constant_
             __syncwarp();
             if (d_issue < ndays) {
                 if (elect_one()) {
+                    fence_proxy_async();       // generic-proxy reads of the stage (above) before the async-proxy overwrite
                     mbar_expect_tx(bar_u + 8u * stage, FB + x_bytes);
                     tma_load_1d(ring_u + stage * SB, fsrc, FB, bar_u + 8u * stage);
                     if (EXT && x_any) tma_load_1d(ring_u + stage * SB + x_dst, vsrc, x_bytes, bar_u + 8u * stage);
@@ -1359,6 +1361,7 @@ __global__ void __launch_bounds__(32 * kEnsParticles, 3) k_ensemble(const __grid
     int n_issue = 0, d_issue = 0;                                 // forcing row and count of the next day to fetch
     auto issue = [&](const uint32_t st) {
         if (elect_one()) {
+            fence_proxy_async();               // generic-proxy reads of the stage before the async-proxy overwrite
             const uint32_t dst = ring_u + st * SB, bar = bar_u + 8u * st;
             const double *v = vtile + (long long)n_issue * v_day;
             mbar_expect_tx(bar, FB + 4u * RB);

@@ -89,8 +89,21 @@ static cudaError_t launch_lean(const RunArgs &a, cudaStream_t st, int ext)
         if (a.P.n_ksub == 3) return launch_lean_nk<20, 3, 3, true>(a, st);
         return launch_lean_nk<20, 2, 0, true>(a, st);
     }
-    if (a.P.n_ksub == 3) return launch_lean_nk<24, 3, 3, false>(a, st);
-    if (a.P.n_ksub == 24) return launch_lean_nk<24, 4, 24, false>(a, st);     // BASELINE configs[1]: trip count known, unrolled by 4
+    if (a.P.n_ksub == 3) {
+        const char *w = getenv("SEMIC_WPC");
+        const int wpc = w ? atoi(w) : 24;
+        if (wpc == 28) return launch_lean_nk<28, 3, 3, false>(a, st);
+        if (wpc == 32) return launch_lean_nk<32, 3, 3, false>(a, st);
+        return launch_lean_nk<24, 3, 3, false>(a, st);
+    }
+    if (a.P.n_ksub == 24) {                                                   // BASELINE configs[1]: trip count known, unrolled by 4
+        const char *w = getenv("SEMIC_WPC");                                  // experiment knob (tools/ab.py): warps per CTA
+        const int wpc = w ? atoi(w) : 24;
+        if (wpc == 16) return launch_lean_nk<16, 4, 24, false>(a, st);
+        if (wpc == 28) return launch_lean_nk<28, 4, 24, false>(a, st);
+        if (wpc == 32) return launch_lean_nk<32, 4, 24, false>(a, st);
+        return launch_lean_nk<24, 4, 24, false>(a, st);
+    }
     if (a.P.n_ksub >= 8) return launch_lean_nk<24, 4, 0, false>(a, st);
     return launch_lean_nk<24, 2, 0, false>(a, st);
 }

@@ -212,10 +212,13 @@ def mass_balance(now, par, bnd, day, year):
 def surface_physics_average(ave, now, step, nt=None):
     """surface_physics_average(ave,now,step,nt), surface_physics.f90:565-597 (device-side).
 
-    The averaged fields live on the device; call ave.download() to look at them on the host.
+    The averaged fields live on the device while the sums run; at step "end" the host mirror of `ave` is refreshed (as the
+    Fortran shim does), so that code written against the f90wrap module can read ave.tsurf right away.
     """
     check(lib().semic_surface_physics_average(ave._require(), now._require(), str(step).encode(),
                                               -1.0 if nt is None else float(nt)))
+    if str(step).strip() == "end":
+        ave.download()
 
 
 def print_param(par):
