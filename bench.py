@@ -498,8 +498,8 @@ def main():
                 barrier()
                 t0 = time.perf_counter()
                 fw = engine.Series(N, 9, args.window)
-                for w in range(args.window):                                               # read_forcing -> device
-                    check(L.semic_series_upload(fw.handle, w, 1, wf_host.array[w % 4].ctypes.data_as(dp_t), N))
+                for w in range(0, args.window, 4):                                         # read_forcing -> device, 4 days per call
+                    check(L.semic_series_upload(fw.handle, w, min(4, args.window - w), wf_host.array.ctypes.data_as(dp_t), N))
                 engine.run(stw, par, bnd, fw, (nloop - 1) * args.days)                     # loops 1 .. nloop-1: no output
                 d2h_rows = 0
                 if daily:
@@ -507,16 +507,17 @@ def main():
                     for d0 in range(0, args.days, 16):
                         nd = min(16, args.days - d0)
                         engine.run(stw, par, bnd, fw, nd, day0=d0 % args.window, out=ring, out_days=nd)
-                        for r in range(nd):
-                            check(L.semic_series_download(ring.handle, r, 1, ho.array[r % 2].ctypes.data_as(dp_t), N, 0, N))
+                        for r in range(0, nd, 2):
+                            check(L.semic_series_download(ring.handle, r, min(2, nd - r), ho.array.ctypes.data_as(dp_t), N, 0, N))
                         d2h_rows += nd
                     ring.free()
                 else:
                     means = engine.Series(N, 8, (args.days + 29) // 30)
                     engine.run(stw, par, bnd, fw, args.days, out=means, out_days=args.days, avg_days=30)
-                    for r in range((args.days + 29) // 30):
-                        check(L.semic_series_download(means.handle, r, 1, ho.array[r % 2].ctypes.data_as(dp_t), N, 0, N))
-                        d2h_rows += 1
+                    nrow = (args.days + 29) // 30
+                    for r in range(0, nrow, 2):
+                        check(L.semic_series_download(means.handle, r, min(2, nrow - r), ho.array.ctypes.data_as(dp_t), N, 0, N))
+                    d2h_rows += nrow
                     means.free()
                 barrier()
                 dt = time.perf_counter() - t0

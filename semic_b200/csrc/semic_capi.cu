@@ -11,6 +11,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <string>
+#include <mutex>
 #include <vector>
 
 #include "semic_b200.h"
@@ -246,15 +247,17 @@ __global__ void k_fill(double *p, int n, double v)
 }
 
 // SoA rows [nd][nvar][ld_soa] (points [p0, p0+np) of the series) <-> tiled series [..][ld/32][nvar][32]
-__global__ void k_soa_to_tiled(const double *soa, long long ld_soa, double *tiled, int ld, int nvar, int day0, int nd, int np)
+__global__ void k_soa_to_tiled(const double *soa, long long ld_soa, double *tiled, int ld, int nvar, int day0, int nd, int np,
+                               int p0 = 0)
 {
     const long long n = (long long)nd * nvar * np;
     for (long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x; k < n; k += (long long)gridDim.x * blockDim.x) {
-        const int i = (int)(k % np);
+        const int j = (int)(k % np);
         const int v = (int)((k / np) % nvar);
         const int d = (int)(k / ((long long)np * nvar));
+        const int i = p0 + j;
         tiled[(((long long)(day0 + d) * (ld / kTile) + i / kTile) * nvar + v) * kTile + (i % kTile)] =
-            soa[((long long)d * nvar + v) * ld_soa + i];
+            soa[((long long)d * nvar + v) * ld_soa + j];
     }
 }
 __global__ void k_tiled_to_soa(const double *tiled, int ld, int nvar, int day0, int nd, int p0, int np, double *soa,
@@ -620,14 +623,45 @@ extern "C" int semic_series_ndays(const semic_series *s) { return s ? s->ndays :
 extern "C" double *semic_series_device_ptr(semic_series *s) { return s ? s->d : nullptr; }
 
 // Host arrays are SoA per day ([ndays][nvar][host_ld], the layout of the reference's files and arrays); the device
-// series is tile-interleaved, so transfers go through a bounded SoA staging buffer and a transpose kernel.
-static int staging_days(int ndays, int nvar, int np)
+// series is tile-interleaved, so transfers go through SoA staging buffers and a transpose kernel.  Units of
+// (one day) x (a slice of points) are double-buffered over a copy stream and a transpose stream, so that the PCIe copy of
+// one unit overlaps the transpose of the previous one; the staging buffers are kept per device between calls.
+namespace {
+struct Staging {
+    double *buf[2] = {nullptr, nullptr};
+    size_t cap = 0;                                  // doubles per buffer
+    cudaStream_t copy = nullptr, conv = nullptr;
+    cudaEvent_t ev_copy[2] = {nullptr, nullptr}, ev_conv[2] = {nullptr, nullptr};
+};
+std::mutex g_stage_mu;
+Staging g_stage[64];
+constexpr int kStageSlice = 1 << 21;                 // points per unit (2 Mi): 151 MB of forcing, 134 MB of output per buffer
+
+cudaError_t staging_get(int device, size_t need, Staging **out)
 {
-    const size_t per_day = (size_t)nvar * (size_t)np * sizeof(double);
-    size_t cap = (256ull << 20) / (per_day ? per_day : 1);
-    if (cap < 1) cap = 1;
-    return (size_t)ndays < cap ? ndays : (int)cap;
+    if (device < 0 || device >= 64) return cudaErrorInvalidDevice;
+    Staging &g = g_stage[device];
+    cudaError_t e;
+    if (!g.copy) {
+        if ((e = cudaStreamCreateWithFlags(&g.copy, cudaStreamNonBlocking)) != cudaSuccess) return e;
+        if ((e = cudaStreamCreateWithFlags(&g.conv, cudaStreamNonBlocking)) != cudaSuccess) return e;
+        for (int b = 0; b < 2; ++b) {
+            if ((e = cudaEventCreateWithFlags(&g.ev_copy[b], cudaEventDisableTiming)) != cudaSuccess) return e;
+            if ((e = cudaEventCreateWithFlags(&g.ev_conv[b], cudaEventDisableTiming)) != cudaSuccess) return e;
+        }
+    }
+    if (g.cap < need) {
+        for (int b = 0; b < 2; ++b) {
+            if (g.buf[b]) cudaFree(g.buf[b]);
+            g.buf[b] = nullptr;
+            if ((e = cudaMalloc(&g.buf[b], need * sizeof(double))) != cudaSuccess) { g.cap = 0; return e; }
+        }
+        g.cap = need;
+    }
+    *out = &g;
+    return cudaSuccess;
 }
+}  // namespace
 
 extern "C" int semic_series_upload(semic_series *s, int day0, int ndays, const double *host, int host_ld)
 {
@@ -637,23 +671,34 @@ extern "C" int semic_series_upload(semic_series *s, int day0, int ndays, const d
     }
     CU(cudaSetDevice(s->device));
     if (ndays == 0 || s->npts == 0) return SEMIC_OK;
-    const int chunk = staging_days(ndays, s->nvar, s->npts);
-    double *tmp = nullptr;
-    CU(cudaMalloc(&tmp, (size_t)chunk * s->nvar * s->npts * sizeof(double)));
-    int rc = SEMIC_OK;
-    for (int d = 0; d < ndays && rc == SEMIC_OK; d += chunk) {
-        const int nd = ndays - d < chunk ? ndays - d : chunk;
-        cudaError_t e = cudaMemcpy2D(tmp, (size_t)s->npts * 8, host + (size_t)d * s->nvar * host_ld, (size_t)host_ld * 8,
-                                     (size_t)s->npts * 8, (size_t)nd * s->nvar, cudaMemcpyHostToDevice);
-        if (e == cudaSuccess) {
-            k_soa_to_tiled<<<1184, 256>>>(tmp, s->npts, s->d, s->ld, s->nvar, day0 + d, nd, s->npts);
-            e = cudaGetLastError();
+    std::lock_guard<std::mutex> lock(g_stage_mu);
+    const int slice = s->npts < kStageSlice ? s->npts : kStageSlice;
+    Staging *g = nullptr;
+    CU(staging_get(s->device, (size_t)s->nvar * slice, &g));
+    CU(cudaDeviceSynchronize());                      // whoever wrote or reads the series before this call is done
+    long long unit = 0;
+    cudaError_t e = cudaSuccess;
+    for (int d = 0; d < ndays && e == cudaSuccess; ++d) {
+        for (int p0 = 0; p0 < s->npts && e == cudaSuccess; p0 += slice, ++unit) {
+            const int b = (int)(unit & 1);
+            const int np = s->npts - p0 < slice ? s->npts - p0 : slice;
+            e = cudaStreamWaitEvent(g->copy, g->ev_conv[b], 0);                     // the transpose that last read buf[b]
+            if (e == cudaSuccess)
+                e = cudaMemcpy2DAsync(g->buf[b], (size_t)np * 8, host + (size_t)d * s->nvar * host_ld + p0, (size_t)host_ld * 8,
+                                      (size_t)np * 8, (size_t)s->nvar, cudaMemcpyHostToDevice, g->copy);
+            if (e == cudaSuccess) e = cudaEventRecord(g->ev_copy[b], g->copy);
+            if (e == cudaSuccess) e = cudaStreamWaitEvent(g->conv, g->ev_copy[b], 0);
+            if (e == cudaSuccess) {
+                k_soa_to_tiled<<<1184, 256, 0, g->conv>>>(g->buf[b], np, s->d, s->ld, s->nvar, day0 + d, 1, np, p0);
+                e = cudaGetLastError();
+            }
+            if (e == cudaSuccess) e = cudaEventRecord(g->ev_conv[b], g->conv);
         }
-        if (e == cudaSuccess) e = cudaDeviceSynchronize();
-        if (e != cudaSuccess) rc = cuda_fail(e, "series_upload");
     }
-    cudaFree(tmp);
-    return rc;
+    if (e == cudaSuccess) e = cudaStreamSynchronize(g->conv);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(g->copy);
+    if (e != cudaSuccess) return cuda_fail(e, "series_upload");
+    return SEMIC_OK;
 }
 extern "C" int semic_series_download(const semic_series *s, int day0, int ndays, double *host, int host_ld, int point0,
                                      int npoints)
@@ -665,21 +710,34 @@ extern "C" int semic_series_download(const semic_series *s, int day0, int ndays,
     }
     CU(cudaSetDevice(s->device));
     if (ndays == 0 || npoints == 0) return SEMIC_OK;
-    const int chunk = staging_days(ndays, s->nvar, npoints);
-    double *tmp = nullptr;
-    CU(cudaMalloc(&tmp, (size_t)chunk * s->nvar * npoints * sizeof(double)));
-    int rc = SEMIC_OK;
-    for (int d = 0; d < ndays && rc == SEMIC_OK; d += chunk) {
-        const int nd = ndays - d < chunk ? ndays - d : chunk;
-        k_tiled_to_soa<<<1184, 256>>>(s->d, s->ld, s->nvar, day0 + d, nd, point0, npoints, tmp, npoints);
-        cudaError_t e = cudaGetLastError();
-        if (e == cudaSuccess)
-            e = cudaMemcpy2D(host + (size_t)d * s->nvar * host_ld, (size_t)host_ld * 8, tmp, (size_t)npoints * 8,
-                             (size_t)npoints * 8, (size_t)nd * s->nvar, cudaMemcpyDeviceToHost);
-        if (e != cudaSuccess) rc = cuda_fail(e, "series_download");
+    std::lock_guard<std::mutex> lock(g_stage_mu);
+    const int slice = npoints < kStageSlice ? npoints : kStageSlice;
+    Staging *g = nullptr;
+    CU(staging_get(s->device, (size_t)s->nvar * slice, &g));
+    CU(cudaDeviceSynchronize());                      // the kernels that wrote the series are done
+    long long unit = 0;
+    cudaError_t e = cudaSuccess;
+    for (int d = 0; d < ndays && e == cudaSuccess; ++d) {
+        for (int q0 = 0; q0 < npoints && e == cudaSuccess; q0 += slice, ++unit) {
+            const int b = (int)(unit & 1);
+            const int np = npoints - q0 < slice ? npoints - q0 : slice;
+            e = cudaStreamWaitEvent(g->conv, g->ev_copy[b], 0);                     // the copy that last read buf[b]
+            if (e == cudaSuccess) {
+                k_tiled_to_soa<<<1184, 256, 0, g->conv>>>(s->d, s->ld, s->nvar, day0 + d, 1, point0 + q0, np, g->buf[b], np);
+                e = cudaGetLastError();
+            }
+            if (e == cudaSuccess) e = cudaEventRecord(g->ev_conv[b], g->conv);
+            if (e == cudaSuccess) e = cudaStreamWaitEvent(g->copy, g->ev_conv[b], 0);
+            if (e == cudaSuccess)
+                e = cudaMemcpy2DAsync(host + (size_t)d * s->nvar * host_ld + q0, (size_t)host_ld * 8, g->buf[b], (size_t)np * 8,
+                                      (size_t)np * 8, (size_t)s->nvar, cudaMemcpyDeviceToHost, g->copy);
+            if (e == cudaSuccess) e = cudaEventRecord(g->ev_copy[b], g->copy);
+        }
     }
-    cudaFree(tmp);
-    return rc;
+    if (e == cudaSuccess) e = cudaStreamSynchronize(g->copy);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(g->conv);
+    if (e != cudaSuccess) return cuda_fail(e, "series_download");
+    return SEMIC_OK;
 }
 
 extern "C" int semic_series_synth_forcing(semic_series *s, uint64_t seed, int64_t point0, int dayofs, int daystride)

@@ -151,7 +151,10 @@ DEVI double fexp_t(double x, const double *tab)
     const double em1 = fma(p23, r2, r);                           // e^r - 1
     const double tj = tab[n & (kExpTab - 1)];
     const double p = fma(em1, tj, tj);
-    return __hiloint2double(__double2hiint(p) + ((n >> 11) << 20), __double2loint(p));
+    // scale by 2^(n >> 11): one shift and one multiply-add on the high word (the compiler's own form is shift, mask, add)
+    int hi;
+    asm("{\n.reg .s32 k;\nshr.s32 k, %1, 11;\nmad.lo.s32 %0, k, 1048576, %2;\n}" : "=r"(hi) : "r"(n), "r"(__double2hiint(p)));
+    return __hiloint2double(hi, __double2loint(p));
 }
 // asin(s) = s + s*z*R(z), z = s*s <= 1/4: degree-11 interpolant of R at the Chebyshev nodes of [0, 1/4]
 // (relative error of asin 5.6e-17 before rounding); coefficients highest degree first
