@@ -8,6 +8,7 @@
 // see semic_b200/driver.py and bench.py).
 // Deviation: every particle starts from the same initial state; the reference carries the state of
 // particle i-1 into particle i.
+#include <chrono>
 #include <cmath>
 #include <sys/stat.h>
 #include <thread>
@@ -92,6 +93,7 @@ int main(int argc, char **argv)
             semic_series_free(fs); semic_series_free(vs);
             check(semic_surface_dealloc(now), "surface_dealloc");                                     // :181
         };
+        const auto t_begin = std::chrono::steady_clock::now();
         if (ndev == 1) {
             run_shard(0);
         } else {
@@ -101,6 +103,9 @@ int main(int argc, char **argv)
         }
         for (int dev = 0; dev < ndev; ++dev)                          // fixed order: reproducible sums
             for (size_t p = 0; p < pars.size(); ++p) sumsq[p] += part[dev][p];
+        const double secs = std::chrono::duration<double>(std::chrono::steady_clock::now() - t_begin).count();
+        std::printf(" " GREEN "run_particle:" RESET " %zu particles x %d points x %d days x %d loops on %d GPU(s): %.3f s "
+                    "(upload, ensemble kernel, download)\n", pars.size(), nx, ntime, d.nloop, ndev, secs);
         for (size_t p = 0; p < pars.size(); ++p) {
             std::snprintf(name, sizeof name, "%s%06d.out", prefix.c_str(), ids[p]);                   // :119-120
             std::FILE *f = std::fopen(name, "w");
