@@ -34,7 +34,7 @@ inline void check(int rc, const char *what)
 // namelist /driver/ nloop, ntime, nx, loi_mask, input_forcing, output, validation
 struct DriverNml {
     int nloop = 0, ntime = 0, nx = 0;
-    int loi_mask[100];
+    std::vector<int> loi_mask;      // loi_mask(100) of the reference; longer here (entries past 100 keep the default) so that nx > 100 runs
     std::string input_forcing, output, validation;
 };
 
@@ -81,7 +81,7 @@ inline DriverNml read_driver_namelist(const std::string &path, int mask_default)
     }
     body = text.substr(g, e - g);
     DriverNml d;
-    for (int &m : d.loi_mask) m = mask_default;                     // example.f90:51, run_particles.f90:61
+    d.loi_mask.assign(100, mask_default);                           // example.f90:51, run_particles.f90:61
     size_t i = 0;
     auto skip = [&]() { while (i < body.size() && (std::isspace((unsigned char)body[i]) || body[i] == ',')) ++i; };
     while (true) {
@@ -148,7 +148,10 @@ inline DriverNml read_driver_namelist(const std::string &path, int mask_default)
             die("namelist &driver: unknown variable " + name);
         }
     }
-    if (d.nx < 1 || d.nx > 100) die("namelist &driver: nx must be in 1..100 (loi_mask(100), example.f90:23)");
+    // the reference stops at nx = 100 (loi_mask(100), example.f90:23, Q13); larger grids run here with the default mask
+    // (2 in example.f90:51 and run_particles.f90:61) beyond point 100 -- an extension, the first 100 points behave alike
+    if (d.nx < 1) die("namelist &driver: nx must be positive");
+    if ((size_t)d.nx > d.loi_mask.size()) d.loi_mask.resize((size_t)d.nx, mask_default);
     if (d.ntime < 1 || d.nloop < 1) die("namelist &driver: ntime and nloop must be positive");
     return d;
 }
