@@ -444,7 +444,7 @@ def main():
         engine.run(st, par24, bnd, forcing, 30, out=out, out_days=30)
         t = min(engine.run(st, par24, bnd, forcing, args.days, out=out, out_days=args.days) for _ in range(2))
         extra["C3_n_ksub24_point_days_per_s"] = float(N) * args.days / (t * 1e-3)
-        extra["C3_n_ksub24_note"] = "same buffers, this rank only; FP64-pipe bound (profiles/r01_summary.md), HBM at ~30 %"
+        extra["C3_n_ksub24_note"] = "same buffers, this rank only; FP64-pipe / issue bound (profiles/r02_summary.md), HBM at ~35 %"
         # C3 with 30-day means instead of daily rows (in-kernel surface_physics_average): 72 + 64/30 B/point-day
         try:
             means = engine.Series(N, 8, 13)

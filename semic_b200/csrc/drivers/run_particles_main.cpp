@@ -93,6 +93,12 @@ int main(int argc, char **argv)
             semic_series_free(fs); semic_series_free(vs);
             check(semic_surface_dealloc(now), "surface_dealloc");                                     // :181
         };
+        {   // bring every device's context up first (in parallel), so that the figure below is the work itself
+            std::vector<std::thread> th;
+            for (int dev = 0; dev < ndev; ++dev)
+                th.emplace_back([dev]() { check(semic_set_device(dev), "set_device"); check(semic_device_synchronize(), "device_synchronize"); });
+            for (auto &t : th) t.join();
+        }
         const auto t_begin = std::chrono::steady_clock::now();
         if (ndev == 1) {
             run_shard(0);

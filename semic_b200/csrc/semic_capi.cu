@@ -633,7 +633,7 @@ struct Staging {
     cudaStream_t copy = nullptr, conv = nullptr;
     cudaEvent_t ev_copy[2] = {nullptr, nullptr}, ev_conv[2] = {nullptr, nullptr};
 };
-std::mutex g_stage_mu;
+std::mutex g_stage_mu[64];                          // one per device: shards on different GPUs transfer concurrently
 Staging g_stage[64];
 constexpr int kStageSlice = 1 << 21;                 // points per unit (2 Mi): 151 MB of forcing, 134 MB of output per buffer
 
@@ -671,7 +671,8 @@ extern "C" int semic_series_upload(semic_series *s, int day0, int ndays, const d
     }
     CU(cudaSetDevice(s->device));
     if (ndays == 0 || s->npts == 0) return SEMIC_OK;
-    std::lock_guard<std::mutex> lock(g_stage_mu);
+    if (s->device < 0 || s->device >= 64) { set_error("series_upload: bad device"); return SEMIC_ERR_ARG; }
+    std::lock_guard<std::mutex> lock(g_stage_mu[s->device]);
     const int slice = s->npts < kStageSlice ? s->npts : kStageSlice;
     Staging *g = nullptr;
     CU(staging_get(s->device, (size_t)s->nvar * slice, &g));
@@ -710,7 +711,8 @@ extern "C" int semic_series_download(const semic_series *s, int day0, int ndays,
     }
     CU(cudaSetDevice(s->device));
     if (ndays == 0 || npoints == 0) return SEMIC_OK;
-    std::lock_guard<std::mutex> lock(g_stage_mu);
+    if (s->device < 0 || s->device >= 64) { set_error("series_download: bad device"); return SEMIC_ERR_ARG; }
+    std::lock_guard<std::mutex> lock(g_stage_mu[s->device]);
     const int slice = npoints < kStageSlice ? npoints : kStageSlice;
     Staging *g = nullptr;
     CU(staging_get(s->device, (size_t)s->nvar * slice, &g));
