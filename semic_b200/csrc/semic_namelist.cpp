@@ -116,7 +116,9 @@ bool to_double(const std::string &t, double &out)
     errno = 0;
     char *end = nullptr;
     out = std::strtod(u.c_str(), &end);
-    return end != u.c_str() && *end == '\0' && errno == 0;
+    if (end == u.c_str() || *end != '\0') return false;
+    // ERANGE on underflow (a subnormal or zero result) is a value Fortran's list-directed input accepts; overflow is an error
+    return errno == 0 || (errno == ERANGE && std::fabs(out) < 1.0);
 }
 
 bool to_int(const std::string &t, int &out)

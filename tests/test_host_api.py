@@ -265,3 +265,17 @@ def test_binary_series_roundtrip_and_ascii_conversion(tmp_path):
     (tmp_path / "bad.bin").write_bytes(b"x" * 100)
     with pytest.raises(ValueError):
         sio.open_series(str(tmp_path / "bad.bin"))
+
+
+def test_namelist_accepts_underflowing_reals_and_rejects_overflow(tmp_path):
+    """a value that underflows to a subnormal is what Fortran's list-directed input stores too; overflow stays an error"""
+    from semic_b200 import surface_physics as sp
+    from semic_b200._capi import SemicError
+    p = tmp_path / "u.nml"
+    p.write_text("&surface_physics\n mcrit = 1.0d-320,\n hcrit = 2.5e-3,\n/\n")
+    par = sp.Surface_Param_Class()
+    sp.surface_physics_par_load(par, str(p))
+    assert par.mcrit == 1e-320 and par.hcrit == 2.5e-3
+    p.write_text("&surface_physics\n mcrit = 1.0d400,\n/\n")
+    with pytest.raises(SemicError):
+        sp.surface_physics_par_load(par, str(p))
