@@ -351,6 +351,14 @@ def main():
     ptdays_step = total_points * args.days
     value = ptdays_step * args.steps / (kernel_ms * 1e-3)
 
+    def maxr_early(vals):
+        if dist is None:
+            return [float(v) for v in vals]
+        import torch
+        t = torch.tensor([float(v) for v in vals], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return [float(x) for x in t]
+
     # ---- end to end: host (pinned) forcing -> H2D -> kernel -> D2H of the daily output, through semic_run_host ----
     e2e = None
     if not args.no_e2e:
@@ -383,6 +391,24 @@ def main():
                "d2h_bytes_per_step": int(N) * args.e2e_days * B_OUT * world,
                "days_per_step": args.e2e_days, "steps": args.e2e_steps, "rank0_cpu_affinity": numa,
                "api": "semic_run_host (pinned host forcing window -> H2D || kernel || D2H of the 8 daily fields, pipelined in units of 1 day x 4 Mi points; PCIe bound: 72 B in + 64 B out per point-day)"}
+        # the same stream with 30-day means as output (semic_run_host, opts.avg_days): D2H shrinks to 64/30 B per point-day
+        if not args.no_extra:
+            try:
+                os.environ["SEMIC_HOST_SLICE"] = str(1 << 20)                 # 30-day units: keep the staging buffers small
+                hm = engine.PinnedArray((2, 8, N))
+                engine.run_host(st, par, bnd, hf.array, 30, h_out=hm.array[:1], out_days=30, chunk_days=30, avg_days=30)
+                barrier()
+                tm = engine.run_host(st, par, bnd, hf.array, 60, h_out=hm.array, out_days=60, chunk_days=30, avg_days=30)
+                barrier()
+                tm = maxr_early([tm])[0]
+                e2e["streamed_with_30_day_means"] = {"value": float(N) * world * 60 / (tm * 1e-3), "unit": "point-days/s",
+                                                     "h2d_bytes_per_step": int(N) * 60 * B_FORCING * world,
+                                                     "d2h_bytes_per_step": int(N) * 2 * B_OUT * world, "days_per_step": 60}
+                hm.free()
+            except Exception as e:
+                e2e["streamed_with_30_day_means_error"] = str(e)[:200]
+            finally:
+                os.environ.pop("SEMIC_HOST_SLICE", None)
         hf.free()
         ho.free()
 

@@ -170,7 +170,9 @@ int semic_run(semic_state *now, const semic_par *par, const semic_bnd *bnd, cons
 
 /* End-to-end variant with HOST buffers: forcing [nwin][9][ldh] (and vali [nwin][8][ldh] or NULL) are streamed
  * host->device in chunks of chunk_days, overlapped with the kernel; the daily output of the last out_days days
- * is streamed back to h_out [out_days][8][ldh].  Host buffers should be pinned (semic_host_alloc). */
+ * is streamed back to h_out [out_days][8][ldh].  Host buffers should be pinned (semic_host_alloc).
+ * opts->avg_days > 1 (plain fast-mode runs): h_out holds ceil(out_days/avg_days) rows, the means over consecutive periods
+ * (surface_physics_average protocol); needs chunk_days % avg_days == 0 and (ndays - out_days) % chunk_days == 0. */
 int semic_run_host(semic_state *now, const semic_par *par, const semic_bnd *bnd, const double *h_forcing,
                    const double *h_vali, int nwin, int ldh, int ndays, double *h_out, int out_days,
                    int chunk_days, const semic_run_opts *opts, float *total_ms);

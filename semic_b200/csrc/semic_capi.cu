@@ -976,6 +976,13 @@ extern "C" int semic_run_host(semic_state *now, const semic_par *par, const semi
     const int ld = now->ld, npts = now->npts;
     const bool generic = any_consulted_flag(bnd) || par->n_ksub < 1;
     const int strict = opts ? opts->strict : 0;
+    // period means instead of daily rows (surface_physics_average protocol, in-kernel): h_out holds ceil(out_days/avg) rows.
+    // Periods must not straddle pipeline units: whole periods per chunk, output starting on a chunk boundary.
+    const int avg = (opts && opts->avg_days > 1 && out_days > 0) ? opts->avg_days : 1;
+    if (avg > 1 && (generic || strict || chunk_days % avg != 0 || (ndays - out_days) % chunk_days != 0)) {
+        set_error("semic_run_host: avg_days needs a plain fast-mode run, chunk_days %% avg_days == 0 and (ndays - out_days) %% chunk_days == 0");
+        return SEMIC_ERR_ARG;
+    }
     const bool use_vali = h_vali != nullptr && generic;
     // point slices: multiples of kLdAlign points, about 4 Mi points each (SEMIC_HOST_SLICE overrides, for tests)
     int slice = 1 << 22;
@@ -1068,11 +1075,13 @@ extern "C" int semic_run_host(semic_state *now, const semic_par *par, const semi
             RunArgs a;
             fill_run_args(a, now, par, bnd, d_ft[b], nd, use_vali ? d_vt[b] : nullptr, 0, nd, d_ot[b], chunk_days, SEMIC_NOUT, o_n);
             a.slab = now->d_slab + p0; a.mask = now->d_mask + p0; a.nx = np; a.sld = sld;      // this slice of the points
+            a.avg_days = avg;
+            const int o_rows = (o_n + avg - 1) / avg;                         // rows this unit writes (= o_n for daily output)
             cudaError_t e = strict ? launch_run_strict(a, generic, now->stream, &launches_total)
                                    : launch_run_fast(a, generic, now->stream, &launches_total);
             if (e != cudaSuccess) { status = cuda_fail(e, "semic_run_host: kernel launch"); cleanup(); return status; }
             if (o_n > 0) {
-                k_tiled_to_soa<<<1184, 256, 0, now->stream>>>(d_ot[b], sld, SEMIC_NOUT, 0, o_n, 0, np, d_os[b], np);
+                k_tiled_to_soa<<<1184, 256, 0, now->stream>>>(d_ot[b], sld, SEMIC_NOUT, 0, o_rows, 0, np, d_os[b], np);
                 CUX(cudaGetLastError());
             }
             if (c == nchunks - 1) {           // the state's forcing fields hold the last day's forcing, as after the reference's loop
@@ -1082,8 +1091,8 @@ extern "C" int semic_run_host(semic_state *now, const semic_par *par, const semi
             CUX(cudaEventRecord(ev_k[b], now->stream));
             if (o_n > 0) {                                                    // D2H of the unit's output days
                 CUX(cudaStreamWaitEvent(s_out, ev_k[b], 0));
-                CUX(cudaMemcpy2DAsync(h_out + (size_t)(o_lo - out_first) * SEMIC_NOUT * ldh + p0, (size_t)ldh * 8, d_os[b],
-                                      (size_t)np * 8, (size_t)np * 8, (size_t)o_n * SEMIC_NOUT, cudaMemcpyDeviceToHost, s_out));
+                CUX(cudaMemcpy2DAsync(h_out + (size_t)((o_lo - out_first) / avg) * SEMIC_NOUT * ldh + p0, (size_t)ldh * 8, d_os[b],
+                                      (size_t)np * 8, (size_t)np * 8, (size_t)o_rows * SEMIC_NOUT, cudaMemcpyDeviceToHost, s_out));
                 CUX(cudaEventRecord(ev_o[b], s_out));
             }
         }

@@ -96,17 +96,20 @@ class PinnedArray(object):
             pass
 
 
-def run_host(state, par, bnd, h_forcing, ndays, h_vali=None, h_out=None, out_days=0, chunk_days=8, strict=False):
+def run_host(state, par, bnd, h_forcing, ndays, h_vali=None, h_out=None, out_days=0, chunk_days=8, strict=False, avg_days=0):
     """semic_run_host: forcing [nwin][9][ldh] (and vali [nwin][8][ldh]) live in HOST memory (numpy arrays or
-    PinnedArray.array); H2D, kernel and D2H are pipelined in chunks of chunk_days.  Returns total ms."""
+    PinnedArray.array); H2D, kernel and D2H are pipelined in chunks of chunk_days.  Returns total ms.
+    avg_days > 1: h_out holds ceil(out_days/avg_days) rows of period means instead of out_days daily rows."""
     nwin, nine, ldh = h_forcing.shape
     assert nine == NFORCING and h_forcing.flags.c_contiguous and h_forcing.dtype == np.float64
     if h_vali is not None:
         assert h_vali.shape == (nwin, NOUT, ldh) and h_vali.flags.c_contiguous
     if out_days > 0:
-        assert h_out is not None and h_out.shape == (out_days, NOUT, ldh) and h_out.flags.c_contiguous
+        rows = out_days if avg_days <= 1 else (out_days + avg_days - 1) // avg_days
+        assert h_out is not None and h_out.shape == (rows, NOUT, ldh) and h_out.flags.c_contiguous
     opts = SemicRunOpts()
     opts.strict = 1 if strict else 0
+    opts.avg_days = int(avg_days)
     ms = C.c_float(0.0)
     check(lib().semic_run_host(state.handle, C.byref(par._c), C.byref(bnd._c), h_forcing.ctypes.data,
                                h_vali.ctypes.data if h_vali is not None else None, nwin, ldh, int(ndays),

@@ -721,6 +721,41 @@ def test_run_host_equals_run(slice_pts, monkeypatch):
     ho.free()
 
 
+def test_run_host_with_period_means(monkeypatch):
+    """semic_run_host with opts.avg_days: the streamed run writes the same period means as the device-resident run with
+    avg_days, which equal the means of the daily rows formed like surface_physics_average does (sum in day order, / n)"""
+    from semic_b200 import engine
+    from semic_b200 import surface_physics as spm
+    g = _gpu()
+    monkeypatch.setenv("SEMIC_HOST_SLICE", "1024")
+    nx, nwin, ndays, out_days, avg, chunk = 2500, 30, 80, 60, 5, 10          # output starts at day 20 = 2 chunks in
+    forc = util.random_forcing(nx, nwin, seed=12)
+    mask = np.full(nx, 2, dtype=np.int32)
+    mask[::5] = 1
+    S0, m0 = util.init_slab(nx, mask)
+    fin_a, out_a, _, _ = g.run_gpu(S0, m0, util.PAR_SLATER, (), forc, ndays, out_days=out_days, branch=False)
+    st = g.make_state(S0, m0)
+    par, bnd = g.make_par(util.PAR_SLATER), g.make_bnd()
+    hf = engine.PinnedArray((nwin, 9, nx))
+    hf.array[...] = forc
+    ho = engine.PinnedArray((out_days // avg, 8, nx))
+    engine.run_host(st, par, bnd, hf.array, ndays, h_out=ho.array, out_days=out_days, chunk_days=chunk, avg_days=avg)
+    st.download()
+    assert np.array_equal(fin_a[:23], st.as_slab()[:23])
+    want = np.zeros((out_days // avg, 8, nx))
+    for p in range(out_days // avg):
+        acc = np.zeros((8, nx))
+        for d in range(avg):
+            acc = acc + out_a[p * avg + d]                                   # field_average 'step' (:614), in day order
+        want[p] = acc / float(avg)                                           # 'end' (:621)
+    assert np.array_equal(ho.array, want)
+    with pytest.raises(Exception):                                           # periods must not straddle pipeline units
+        engine.run_host(st, par, bnd, hf.array, ndays, h_out=ho.array, out_days=out_days, chunk_days=8, avg_days=avg)
+    spm.surface_dealloc(st)
+    hf.free()
+    ho.free()
+
+
 @pytest.mark.parametrize("names", [("tsurf", "alb"), ("melt", "acc")])
 def test_run_host_with_external_fields_equals_run(names, monkeypatch):
     """host-streamed run with boundary overrides fed from a HOST validation window (point slices + day chunks)"""
