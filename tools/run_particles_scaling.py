@@ -6,8 +6,18 @@ particle) into a scratch directory and runs semic_b200/bin/run_particles.x twice
 import os, re, subprocess, sys, tempfile, time
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np
-from tests import util
-from oracle import ref_binding as rb          # only its namelist writer (file format of optimize/tools.py)
+import bench                                   # parameter values and the synthetic forcing generator of the product side
+from semic_b200 import synth
+
+
+def write_namelist(path, par_d):
+    """one particle's &surface_physics group, the file format optimize/tools.py:7-43 writes"""
+    with open(path, "w") as f:
+        f.write('&surface_physics\n  boundary = "" "" "",\n')
+        for k in sorted(par_d):
+            v = par_d[k]
+            f.write("  %s = %s,\n" % (k, '"%s"' % v if isinstance(v, str) else ("%d" % v if isinstance(v, int) else repr(float(v)))))
+        f.write("/\n")
 
 nx = int(sys.argv[1]) if len(sys.argv) > 1 else 4096
 P = int(sys.argv[2]) if len(sys.argv) > 2 else 1024
@@ -16,7 +26,7 @@ root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 exe = os.path.join(root, "semic_b200", "bin", "run_particles.x")
 d = tempfile.mkdtemp()
 t0 = time.time()
-forc = util.random_forcing(nx, 365, seed=3)
+forc = synth.forcing(nx, 365)
 r = np.random.default_rng(1)
 vali = r.normal(size=(365, 8, nx)) * np.array([5, .1, 30, 1e-8, 1e-8, 1e-8, 5, 5])[None, :, None] + \
     np.array([260, .7, 60, 0, 1e-8, 1e-8, 0, 0])[None, :, None]
@@ -25,9 +35,9 @@ np.savetxt(os.path.join(d, "vali.txt"), vali.reshape(365, -1), fmt="%.7g")
 with open(os.path.join(d, "optimization.namelist"), "w") as f:
     f.write('&driver\n nloop = %d,\n ntime = 365,\n nx = %d,\n input_forcing = "forcing.txt",\n validation = "vali.txt",\n/\n' % (nloop, nx))
 for i in range(P):
-    pd = dict(util.PAR_SLATER, alb_scheme="none", hcrit=0.02 + 0.4 * r.uniform(), amp=1.0 + 3 * r.uniform(), rcrit=r.uniform(),
+    pd = dict(bench.par_dict("none", 3), hcrit=0.02 + 0.4 * r.uniform(), amp=1.0 + 3 * r.uniform(), rcrit=r.uniform(),
               albi=0.35 + 0.2 * r.uniform(), albl=0.05 + 0.3 * r.uniform(), alb_smax=0.8 + 0.1 * r.uniform())
-    rb.write_namelist(os.path.join(d, "p_%06d.nml" % i), pd)
+    write_namelist(os.path.join(d, "p_%06d.nml" % i), pd)
 print("inputs written in %.1f s (%d points, %d particles, nloop %d)" % (time.time() - t0, nx, P, nloop), flush=True)
 res = {}
 for label, env in (("1 GPU", dict(os.environ, CUDA_VISIBLE_DEVICES="0")), ("all GPUs", dict(os.environ))):
