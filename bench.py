@@ -643,8 +643,8 @@ def main():
                 return make_state(n, p0_, 0.90, 0.10), f_, o_
 
             st5, f5, o5 = ens_inputs(n5, lo5)
-            comm = None
-            if world > 1:
+
+            def make_comm():
                 import torch
                 uid = C.create_string_buffer(128)
                 if rank == 0:
@@ -652,27 +652,48 @@ def main():
                 t = torch.tensor(list(uid.raw), dtype=torch.uint8, device="cuda")
                 dist.broadcast(t, 0)
                 uid = C.create_string_buffer(bytes(t.cpu().tolist()), 128)
-                comm = C.c_void_p()
-                check(L.semic_comm_init(C.byref(comm), uid, world, rank))
-            engine.ensemble_cost(st5, pars[:8], bnd, f5, o5, 365, 1, comm=comm)
-            best, best_ar, sumsq = None, None, None
-            for _ in range(2):
-                barrier()
-                sumsq, kms = engine.ensemble_cost(st5, pars, bnd, f5, o5, 365, 1, comm=comm)
-                ar = C.c_float(0.0)
-                if comm is not None:
-                    check(L.semic_comm_last_allreduce_ms(comm, C.byref(ar)))
-                tot = maxr([kms + ar.value])[0]
-                kmax = maxr([kms])[0]
-                armin = minr([ar.value])[0]
-                if best is None or tot < best:
-                    best, best_ar, best_k = tot, armin, kmax
+                cm = C.c_void_p()
+                check(L.semic_comm_init(C.byref(cm), uid, world, rank))
+                return cm
+
+            def time_ensemble(cm):
+                engine.ensemble_cost(st5, pars[:8], bnd, f5, o5, 365, 1, comm=cm)
+                best_, ar_, k_, sums_ = None, None, None, None
+                for _ in range(2):
+                    barrier()
+                    sums_, kms = engine.ensemble_cost(st5, pars, bnd, f5, o5, 365, 1, comm=cm)
+                    ar = C.c_float(0.0)
+                    if cm is not None:
+                        check(L.semic_comm_last_allreduce_ms(cm, C.byref(ar)))
+                    tot = maxr([kms + ar.value])[0]
+                    kmax = maxr([kms])[0]
+                    armin = minr([ar.value])[0]
+                    if best_ is None or tot < best_:
+                        best_, ar_, k_ = tot, armin, kmax
+                return best_, ar_, k_, sums_
+
+            comm = make_comm() if world > 1 else None
+            fused = bool(comm is not None and L.semic_comm_p2p(comm, None, 0))
+            best, best_ar, best_k, sumsq = time_ensemble(comm)
             extra["C5_ensemble_1024x100k_trajectory_days_per_s"] = float(P) * NX * 365 / (best * 1e-3)
             extra["C5_ms"] = best
             extra["C5_kernel_ms_max_over_ranks"] = best_k
             extra["C5_allreduce_ms"] = best_ar
-            extra["C5_note"] = ("points sharded over %d rank(s); kernel + all-reduce device time, max over ranks; all-reduce = ncclAllReduce(sum, 1024 f64) "
-                                "through semic_comm (the fastest rank's figure: the others include waiting for the slowest kernel)" % world)
+            extra["C5_collective"] = ("none (1 rank)" if comm is None else
+                                      "second reduction stage + sum over the ranks in ONE kernel over NVLink peer memory (k_ens_reduce_p2p)" if fused
+                                      else "ncclAllReduce(sum, 1024 f64) through semic_comm")
+            extra["C5_note"] = ("points sharded over %d rank(s); trajectory kernel + reduction/exchange device time, max over ranks; "
+                                "C5_allreduce_ms = the exchange on the fastest rank (the others include waiting for the slowest kernel)" % world)
+            if fused:                                                                      # NCCL's all-reduce beside it, same inputs
+                os.environ["SEMIC_COMM_P2P"] = "0"
+                comm_n = make_comm()
+                os.environ.pop("SEMIC_COMM_P2P", None)
+                b_n, ar_n, _, sums_n = time_ensemble(comm_n)
+                extra["C5_ms_with_nccl_allreduce"] = b_n
+                extra["C5_nccl_allreduce_ms"] = ar_n
+                fin_ = np.isfinite(sumsq) & np.isfinite(sums_n)
+                extra["C5_peer_memory_vs_nccl_max_rel_diff"] = float(np.max(np.abs(sumsq[fin_] - sums_n[fin_]) / np.abs(sums_n[fin_]))) if fin_.any() else None
+                check(L.semic_comm_free(comm_n))
             if world > 1:
                 # in-run check: the reduced sums equal a single-GPU evaluation of the WHOLE grid (first 16 particles)
                 if rank == 0:

@@ -193,6 +193,10 @@ int semic_ensemble_cost(const semic_state *init, const semic_par *pars, int npar
 int semic_comm_unique_id(char id[128]);                                   /* ncclGetUniqueId */
 int semic_comm_init(semic_comm **c, const char id[128], int nranks, int rank);   /* ncclCommInitRank on the current device */
 int semic_comm_allreduce_sum(semic_comm *c, double *dev_buf, int count);  /* in place, on the comm's stream, synchronises */
+/* 1 if the communicator exchanges through NVLink peer memory (CUDA IPC mappings of every rank's buffer; the all-reduce of
+ * semic_ensemble_cost is then part of its reduction kernel), 0 if through ncclAllReduce; `why` receives the reason for 0.
+ * Env SEMIC_COMM_P2P=0 at semic_comm_init keeps NCCL (all ranks alike). */
+int semic_comm_p2p(const semic_comm *c, char *why, int why_len);
 int semic_comm_last_allreduce_ms(const semic_comm *c, float *ms);         /* device time (CUDA events on the comm's stream) of the last all-reduce */
 int semic_comm_free(semic_comm *c);
 

@@ -111,6 +111,7 @@ PROTOTYPES = {
     "semic_comm_init": (C.c_int, [C.POINTER(_vp), C.c_char_p, C.c_int, C.c_int]),
     "semic_comm_allreduce_sum": (C.c_int, [_vp, _vp, C.c_int]),
     "semic_comm_last_allreduce_ms": (C.c_int, [_vp, C.POINTER(C.c_float)]),
+    "semic_comm_p2p": (C.c_int, [_vp, C.c_char_p, C.c_int]),
     "semic_comm_free": (C.c_int, [_vp]),
     "semic_set_device": (C.c_int, [C.c_int]),
     "semic_device_count": (C.c_int, []),

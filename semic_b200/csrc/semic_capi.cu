@@ -144,6 +144,17 @@ struct semic_comm {
     cudaEvent_t e0 = nullptr, e1 = nullptr;      // around the last all-reduce, on `stream`
     float last_ms = 0.f;
     int nranks = 1, rank = 0;
+    // peer-memory exchange (NVLink): every rank's buffer [2 flags | 2 x kP2PMaxPar doubles] mapped on every rank through CUDA IPC
+    bool p2p_ready = false;
+    char p2p_why[160] = "";                      // why the peer-memory path is off (then the all-reduce is NCCL's)
+    void *p2p_own = nullptr;                     // this rank's buffer
+    std::vector<void *> p2p_peer;                // mapped peers (own entry = p2p_own)
+    double **d_data = nullptr;                   // device arrays of the per-rank pointers
+    unsigned long long **d_flags = nullptr;
+    unsigned *d_done = nullptr;
+    int *d_err = nullptr;
+    unsigned long long epoch = 0;
+    int device = 0;
 };
 
 static inline int round_up(int v, int m) { return (v + m - 1) / m * m; }
@@ -1206,6 +1217,7 @@ struct NcclApi {
     ncclResult_t (*GetUniqueId)(ncclUniqueId *) = nullptr;
     ncclResult_t (*CommInitRank)(ncclComm_t *, int, ncclUniqueId, int) = nullptr;
     ncclResult_t (*AllReduce)(const void *, void *, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*AllGather)(const void *, void *, size_t, ncclDataType_t, ncclComm_t, cudaStream_t) = nullptr;
     ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
     const char *(*GetErrorString)(ncclResult_t) = nullptr;
 };
@@ -1221,6 +1233,7 @@ int nccl_load()
     g_nccl.GetUniqueId = (decltype(g_nccl.GetUniqueId))dlsym(h, "ncclGetUniqueId");
     g_nccl.CommInitRank = (decltype(g_nccl.CommInitRank))dlsym(h, "ncclCommInitRank");
     g_nccl.AllReduce = (decltype(g_nccl.AllReduce))dlsym(h, "ncclAllReduce");
+    g_nccl.AllGather = (decltype(g_nccl.AllGather))dlsym(h, "ncclAllGather");
     g_nccl.CommDestroy = (decltype(g_nccl.CommDestroy))dlsym(h, "ncclCommDestroy");
     g_nccl.GetErrorString = (decltype(g_nccl.GetErrorString))dlsym(h, "ncclGetErrorString");
     if (!g_nccl.GetUniqueId || !g_nccl.CommInitRank || !g_nccl.AllReduce || !g_nccl.CommDestroy) {
@@ -1236,6 +1249,110 @@ int nccl_fail(ncclResult_t r, const char *what)
     return SEMIC_ERR_NCCL;
 }
 }  // namespace
+
+// Peer-memory set-up: allocate this rank's exchange buffer, hand its IPC handle to every rank (ncclAllGather of the 64 handle
+// bytes), map the peers' buffers, and agree (ncclAllReduce, min) on whether EVERY rank succeeded -- the ranks must take the same
+// path or they would wait for each other forever.  SEMIC_COMM_P2P=0 keeps NCCL's all-reduce (the baseline to compare with).
+static void p2p_setup(semic_comm *c)
+{
+    auto off = [&](const char *why) { std::snprintf(c->p2p_why, sizeof c->p2p_why, "%s", why); };
+    const char *env = getenv("SEMIC_COMM_P2P");
+    int want = !(env && std::strcmp(env, "0") == 0) && g_nccl.AllGather != nullptr;
+    const size_t bytes = 128 + 2 * (size_t)kP2PMaxPar * sizeof(double);
+    int ok = want;
+    cudaIpcMemHandle_t mine;
+    std::memset(&mine, 0, sizeof mine);
+    if (ok && (cudaMalloc(&c->p2p_own, bytes) != cudaSuccess || cudaMemset(c->p2p_own, 0, bytes) != cudaSuccess ||
+               cudaDeviceSynchronize() != cudaSuccess || cudaIpcGetMemHandle(&mine, c->p2p_own) != cudaSuccess)) {
+        ok = 0;
+        cudaGetLastError();
+    }
+    // exchange handles and "ok so far" in one all-gather: [64 handle bytes][1 ok byte][pad] per rank
+    const size_t rec = 72;
+    std::vector<unsigned char> all(rec * (size_t)c->nranks, 0), me(rec, 0);
+    std::memcpy(me.data(), &mine, sizeof mine);
+    me[64] = (unsigned char)ok;
+    unsigned char *d_me = nullptr, *d_all = nullptr;
+    bool gathered = false;
+    if (cudaMalloc(&d_me, rec) == cudaSuccess && cudaMalloc(&d_all, rec * (size_t)c->nranks) == cudaSuccess &&
+        cudaMemcpy(d_me, me.data(), rec, cudaMemcpyHostToDevice) == cudaSuccess && g_nccl.AllGather &&
+        g_nccl.AllGather(d_me, d_all, rec, ncclChar, c->comm, c->stream) == ncclSuccess &&
+        cudaStreamSynchronize(c->stream) == cudaSuccess &&
+        cudaMemcpy(all.data(), d_all, rec * (size_t)c->nranks, cudaMemcpyDeviceToHost) == cudaSuccess)
+        gathered = true;
+    if (d_me) cudaFree(d_me);
+    if (d_all) cudaFree(d_all);
+    if (!gathered) { off("handle exchange failed"); ok = 0; }
+    for (int r = 0; ok && r < c->nranks; ++r) if (!all[rec * (size_t)r + 64]) ok = 0;      // somebody opted out or failed
+    c->p2p_peer.assign((size_t)c->nranks, nullptr);
+    for (int r = 0; ok && r < c->nranks; ++r) {
+        if (r == c->rank) { c->p2p_peer[(size_t)r] = c->p2p_own; continue; }
+        cudaIpcMemHandle_t h;
+        std::memcpy(&h, all.data() + rec * (size_t)r, sizeof h);
+        if (cudaIpcOpenMemHandle(&c->p2p_peer[(size_t)r], h, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) {
+            ok = 0;
+            cudaGetLastError();
+            off("cudaIpcOpenMemHandle failed (no peer access between the GPUs?)");
+        }
+    }
+    if (ok) {
+        std::vector<double *> hd((size_t)c->nranks);
+        std::vector<unsigned long long *> hf((size_t)c->nranks);
+        for (int r = 0; r < c->nranks; ++r) {
+            hf[(size_t)r] = reinterpret_cast<unsigned long long *>(c->p2p_peer[(size_t)r]);
+            hd[(size_t)r] = reinterpret_cast<double *>(reinterpret_cast<char *>(c->p2p_peer[(size_t)r]) + 128);
+        }
+        if (cudaMalloc(&c->d_data, sizeof(double *) * (size_t)c->nranks) != cudaSuccess ||
+            cudaMalloc(&c->d_flags, sizeof(unsigned long long *) * (size_t)c->nranks) != cudaSuccess ||
+            cudaMalloc(&c->d_done, sizeof(unsigned)) != cudaSuccess || cudaMalloc(&c->d_err, sizeof(int)) != cudaSuccess ||
+            cudaMemcpy(c->d_data, hd.data(), sizeof(double *) * (size_t)c->nranks, cudaMemcpyHostToDevice) != cudaSuccess ||
+            cudaMemcpy(c->d_flags, hf.data(), sizeof(unsigned long long *) * (size_t)c->nranks, cudaMemcpyHostToDevice) != cudaSuccess ||
+            cudaMemset(c->d_done, 0, sizeof(unsigned)) != cudaSuccess || cudaMemset(c->d_err, 0, sizeof(int)) != cudaSuccess ||
+            cudaDeviceSynchronize() != cudaSuccess) {
+            ok = 0;
+            cudaGetLastError();
+            off("device tables");
+        }
+    }
+    // agree: every rank must have mapped every peer
+    {
+        int *d_ok = nullptr;
+        int h_ok = ok;
+        bool agreed = false;
+        if (cudaMalloc(&d_ok, sizeof(int)) == cudaSuccess && cudaMemcpy(d_ok, &h_ok, sizeof(int), cudaMemcpyHostToDevice) == cudaSuccess &&
+            g_nccl.AllReduce(d_ok, d_ok, 1, ncclInt32, ncclMin, c->comm, c->stream) == ncclSuccess &&
+            cudaStreamSynchronize(c->stream) == cudaSuccess && cudaMemcpy(&h_ok, d_ok, sizeof(int), cudaMemcpyDeviceToHost) == cudaSuccess)
+            agreed = true;
+        if (d_ok) cudaFree(d_ok);
+        if (!agreed) h_ok = 0;
+        if (ok && !h_ok) off("another rank could not map its peers");
+        ok = h_ok;
+    }
+    if (!want && !c->p2p_why[0]) off(env ? "SEMIC_COMM_P2P=0" : "ncclAllGather not available");
+    if (!ok && !c->p2p_why[0]) off("peer-memory set-up failed on a rank");
+    c->p2p_ready = ok != 0;
+}
+
+// for semic_ensemble.cu: the arguments of the fused reduction + exchange kernel for the NEXT exchange, or false
+namespace semic {
+bool comm_p2p_next(semic_comm *c, int npar, P2PArgs *a)
+{
+    if (!c || !c->p2p_ready || npar > kP2PMaxPar) return false;
+    ++c->epoch;
+    a->data = c->d_data; a->flags = c->d_flags; a->done = c->d_done; a->err = c->d_err;
+    a->nranks = c->nranks; a->rank = c->rank; a->epoch = c->epoch;
+    a->timeout_cycles = 20LL * 1000 * 1000 * 1000;           // ~10 s at 2 GHz: a missing peer is an error, not a hang
+    return true;
+}
+int comm_p2p_check(semic_comm *c, float ms)
+{
+    int err = 0;
+    if (cudaMemcpy(&err, c->d_err, sizeof(int), cudaMemcpyDeviceToHost) != cudaSuccess) err = 1;
+    c->last_ms = ms;
+    if (err) { set_error("peer-memory exchange: a rank did not arrive within the time-out"); return SEMIC_ERR_NCCL; }
+    return SEMIC_OK;
+}
+}  // namespace semic
 
 extern "C" int semic_comm_unique_id(char id[128])
 {
@@ -1264,8 +1381,16 @@ extern "C" int semic_comm_init(semic_comm **out, const char id[128], int nranks,
     if ((e = cudaEventCreate(&c->e0)) != cudaSuccess || (e = cudaEventCreate(&c->e1)) != cudaSuccess) {
         g_nccl.CommDestroy(c->comm); cudaStreamDestroy(c->stream); delete c; return cuda_fail(e, "comm_init: events");
     }
+    cudaGetDevice(&c->device);
+    p2p_setup(c);                                 // optional: without it the exchange is NCCL's all-reduce
     *out = c;
     return SEMIC_OK;
+}
+extern "C" int semic_comm_p2p(const semic_comm *c, char *why, int why_len)
+{
+    if (!c) return 0;
+    if (why && why_len > 0) std::snprintf(why, (size_t)why_len, "%s", c->p2p_why);
+    return c->p2p_ready ? 1 : 0;
 }
 extern "C" int semic_comm_allreduce_sum(semic_comm *c, double *dev_buf, int count)
 {
@@ -1287,6 +1412,23 @@ extern "C" int semic_comm_last_allreduce_ms(const semic_comm *c, float *ms)
 extern "C" int semic_comm_free(semic_comm *c)
 {
     if (!c) { set_error("comm_free: null"); return SEMIC_ERR_ARG; }
+    cudaSetDevice(c->device);
+    if (c->p2p_ready) {
+        // collective: nobody unmaps or frees while a peer may still be reading (one tiny all-reduce as the barrier)
+        int *d_one = nullptr;
+        if (cudaMalloc(&d_one, sizeof(int)) == cudaSuccess && cudaMemset(d_one, 0, sizeof(int)) == cudaSuccess) {
+            g_nccl.AllReduce(d_one, d_one, 1, ncclInt32, ncclSum, c->comm, c->stream);
+            cudaStreamSynchronize(c->stream);
+        }
+        if (d_one) cudaFree(d_one);
+    }
+    for (int r = 0; r < (int)c->p2p_peer.size(); ++r)
+        if (c->p2p_peer[(size_t)r] && c->p2p_peer[(size_t)r] != c->p2p_own) cudaIpcCloseMemHandle(c->p2p_peer[(size_t)r]);
+    if (c->d_data) cudaFree(c->d_data);
+    if (c->d_flags) cudaFree(c->d_flags);
+    if (c->d_done) cudaFree(c->d_done);
+    if (c->d_err) cudaFree(c->d_err);
+    if (c->p2p_own) cudaFree(c->p2p_own);
     if (c->e0) cudaEventDestroy(c->e0);
     if (c->e1) cudaEventDestroy(c->e1);
     if (c->stream) cudaStreamDestroy(c->stream);

@@ -13,6 +13,8 @@ DevPar make_devpar_public(const semic_par *par);
 bool any_consulted_flag_public(const semic_bnd *b);
 int state_info(const semic_state *s, int *npts, int *ld, int *device, double **d_slab, int **d_mask, cudaStream_t *stream);
 int series_info(const semic_series *s, int *npts, int *ld, int *nvar, int *ndays, double **d);
+bool comm_p2p_next(semic_comm *c, int npar, P2PArgs *a);
+int comm_p2p_check(semic_comm *c, float ms);
 }  // namespace semic
 using namespace semic;
 
@@ -37,9 +39,11 @@ extern "C" int semic_ensemble_cost(const semic_state *init, const semic_par *par
     cudaStream_t st = nullptr;
     double *d_invvar = nullptr, *d_partial = nullptr, *d_sumsq = nullptr;
     DevPar *d_pars = nullptr;
-    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    cudaEvent_t e0 = nullptr, e1 = nullptr, emid = nullptr;
     std::vector<DevPar> hp;
     EnsArgs a;
+    P2PArgs p2p;
+    bool use_p2p = false;
 
     if (!init || !pars || npar <= 0 || !bnd || !forcing || !vali || ntime <= 0 || nloop <= 0 || !sumsq) {
         set_error("semic_ensemble_cost: bad arguments");
@@ -90,15 +94,27 @@ extern "C" int semic_ensemble_cost(const semic_state *init, const semic_par *par
         if (hp[p].scheme != a.uni_scheme) a.uni_scheme = -1;
         if (hp[p].n_ksub != a.uni_ksub) a.uni_ksub = 0;
     }
-    if (npts > 0) {
-        CUE(launch_vali_invvar(a, d_invvar, st));
+    // The one collective of the path (sum over the shards).  With a peer-memory communicator it is part of the second
+    // reduction stage (k_ens_reduce_p2p: every rank adds the ranks' sums over NVLink in rank order); otherwise NCCL's all-reduce.
+    use_p2p = comm != nullptr && comm_p2p_next(comm, npar, &p2p);
+    CUE(cudaEventCreate(&emid));
+    if (npts > 0 || use_p2p) {
+        if (npts > 0) CUE(launch_vali_invvar(a, d_invvar, st));
         CUE(cudaEventRecord(e0, st));
-        CUE(launch_ensemble_fast(a, d_sumsq, st));
+        CUE(launch_ensemble_fast(a, d_sumsq, st, use_p2p ? &p2p : nullptr, emid));
         CUE(cudaEventRecord(e1, st));
         CUE(cudaStreamSynchronize(st));
-        if (kernel_ms) CUE(cudaEventElapsedTime(kernel_ms, e0, e1));
+        if (use_p2p) {                            // kernel_ms = the trajectories; the reduction + exchange is the communicator's figure
+            float ex = 0.f;
+            if (kernel_ms) CUE(cudaEventElapsedTime(kernel_ms, e0, emid));
+            CUE(cudaEventElapsedTime(&ex, emid, e1));
+            const int rc = comm_p2p_check(comm, ex);
+            if (rc) { status = rc; goto done; }
+        } else if (kernel_ms) {
+            CUE(cudaEventElapsedTime(kernel_ms, e0, e1));
+        }
     }
-    if (comm) {                                   // the one collective of the path: sum over shards
+    if (comm && !use_p2p) {
         const int rc = semic_comm_allreduce_sum(comm, d_sumsq, npar);
         if (rc) { status = rc; goto done; }
     }
@@ -110,5 +126,6 @@ done:
     if (d_pars) cudaFree(d_pars);
     if (e0) cudaEventDestroy(e0);
     if (e1) cudaEventDestroy(e1);
+    if (emid) cudaEventDestroy(emid);
     return status;
 }

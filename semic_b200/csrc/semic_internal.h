@@ -108,6 +108,19 @@ struct EnsArgs {
     int           uni_ksub;     // the n_ksub all particles share, or 0
 };
 
+// Peer-memory exchange of the ensemble's per-particle sums (NVLink / NVSwitch, one process per GPU).  Every rank owns a buffer
+// [2 flags][2 slots][kP2PMaxPar doubles] that all ranks have mapped (CUDA IPC); slot = epoch & 1.
+constexpr int kP2PMaxPar = 65536;
+struct P2PArgs {
+    double *const *data;                    // device array [nranks]: base of rank r's two slots
+    unsigned long long *const *flags;       // device array [nranks]: rank r's two epoch flags
+    unsigned *done;                         // this rank's CTA counter (zero between launches)
+    int *err;                               // set to 1 if a peer did not arrive in time
+    int nranks, rank;
+    unsigned long long epoch;               // > 0, the same on every rank
+    long long timeout_cycles;
+};
+
 // one-time per-device set-up of the fast arithmetic (the 2^(j/2048) table); cheap no-op afterwards.  The launchers call it
 // themselves; timed entry points call it before their first event so that it never lands inside a timed region
 cudaError_t prepare_fast();
@@ -116,7 +129,10 @@ cudaError_t launch_run_fast(const RunArgs &a, bool generic, cudaStream_t st, int
 cudaError_t launch_run_strict(const RunArgs &a, bool generic, cudaStream_t st, int *launches);
 // inv_var and partial are scratch buffers owned by the caller; sumsq_dev receives npar doubles
 cudaError_t launch_vali_invvar(const EnsArgs &a, double *inv_var, cudaStream_t st);
-cudaError_t launch_ensemble_fast(const EnsArgs &a, double *sumsq_dev, cudaStream_t st);
+// p2p != NULL: the second reduction stage also sums over the ranks through peer memory (k_ens_reduce_p2p) and sumsq_dev
+// receives the GLOBAL sums; mid (may be NULL) is recorded between the trajectory kernel and the reduction
+cudaError_t launch_ensemble_fast(const EnsArgs &a, double *sumsq_dev, cudaStream_t st, const P2PArgs *p2p = nullptr,
+                                 cudaEvent_t mid = nullptr);
 cudaError_t launch_elementals_fast(int which, const double *const *in, const int *mask, const double *sc,
                                    double *const *out, int n, cudaStream_t st);
 

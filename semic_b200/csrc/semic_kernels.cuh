@@ -1460,6 +1460,68 @@ __global__ void k_ens_reduce(const double *partial, int ntiles, int npar, double
     for (int t = 0; t < ntiles; ++t) acc += partial[(long long)p * ntiles + t];
     sumsq[p] = acc;
 }
+// ------------------------------------------------------------------------------------------------
+// second stage + the one collective of the path in ONE kernel, over NVLink peer memory
+// ------------------------------------------------------------------------------------------------
+// Replaces k_ens_reduce followed by ncclAllReduce (optimize/run_particles.f90:171-177 + tools.py:58-62: the per-particle
+// sums of all shards).  Every CTA reduces its particles over the local tiles into this rank's peer-visible slot; the last
+// CTA to finish publishes the slot (release store of the epoch, system scope); every CTA then waits for the epoch flag of
+// every rank (acquire loads through the NVLink mapping, nanosleep back-off, bounded by a time-out) and adds the ranks' values
+// in rank order -- every rank computes the same bits.  Slots alternate with the epoch: a rank can only be two epochs ahead
+// of a peer after that peer has finished reading, so no second handshake is needed.
+DEVI void st_release_sys_u64(unsigned long long *p, unsigned long long v)
+{
+    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+DEVI unsigned long long ld_acquire_sys_u64(const unsigned long long *p)
+{
+    unsigned long long v;
+    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+DEVI double ld_relaxed_sys_f64(const double *p)
+{
+    double v;
+    asm volatile("ld.relaxed.sys.global.f64 %0, [%1];" : "=d"(v) : "l"(p) : "memory");
+    return v;
+}
+
+__global__ void k_ens_reduce_p2p(const double *partial, int ntiles, int npar, double *sumsq, const P2PArgs p)
+{
+    __shared__ int s_bad;
+    const int q = blockIdx.x * blockDim.x + threadIdx.x;
+    const int slot = (int)(p.epoch & 1ull);
+    double *mine = p.data[p.rank] + (size_t)slot * kP2PMaxPar;
+    if (threadIdx.x == 0) s_bad = 0;
+    if (q < npar) {
+        double acc = 0.0;
+        for (int t = 0; t < ntiles; ++t) acc += partial[(long long)q * ntiles + t];      // fixed order, as k_ens_reduce
+        mine[q] = acc;
+    }
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const unsigned prev = atomicAdd(p.done, 1u);
+        if (prev == gridDim.x - 1) {                    // every CTA of this rank has written its part
+            *p.done = 0u;
+            __threadfence_system();
+            st_release_sys_u64(p.flags[p.rank] + slot, p.epoch);
+        }
+    }
+    if (threadIdx.x < p.nranks) {
+        const unsigned long long *f = p.flags[threadIdx.x] + slot;
+        const long long t0 = clock64();
+        while (ld_acquire_sys_u64(f) < p.epoch) {
+            if (clock64() - t0 > p.timeout_cycles) { s_bad = 1; atomicExch(p.err, 1); break; }
+            __nanosleep(100);
+        }
+    }
+    __syncthreads();
+    if (s_bad || q >= npar) return;
+    double sum = 0.0;
+    for (int r = 0; r < p.nranks; ++r) sum += ld_relaxed_sys_f64(p.data[r] + (size_t)slot * kP2PMaxPar + q);
+    sumsq[q] = sum;
+}
 #endif  // !SEMIC_STRICT
 
 #undef BND

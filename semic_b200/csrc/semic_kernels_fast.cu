@@ -94,9 +94,15 @@ cudaError_t launch_vali_invvar(const EnsArgs &a, double *inv_var, cudaStream_t s
     return cudaGetLastError();
 }
 
-cudaError_t launch_ensemble_fast(const EnsArgs &a, double *sumsq_dev, cudaStream_t st)
+cudaError_t launch_ensemble_fast(const EnsArgs &a, double *sumsq_dev, cudaStream_t st, const P2PArgs *p2p, cudaEvent_t mid)
 {
-    if (a.nx <= 0 || a.npar <= 0) return cudaSuccess;
+    if (a.npar <= 0) return cudaSuccess;
+    if (a.nx <= 0) {                                    // a rank without points still takes part in the exchange (zeros)
+        if (!p2p) return cudaSuccess;
+        if (mid) { if (cudaError_t e = cudaEventRecord(mid, st)) return e; }
+        fast_mode::k_ens_reduce_p2p<<<(a.npar + 127) / 128, 128, 0, st>>>(a.partial, 0, a.npar, sumsq_dev, *p2p);
+        return cudaGetLastError();
+    }
     if (cudaError_t e = ensure_exp_table()) return e;
     const int ngroups = (a.npar + fast_mode::kEnsParticles - 1) / fast_mode::kEnsParticles;
     const long long nblocks = (long long)a.ntiles * ngroups;
@@ -114,7 +120,9 @@ cudaError_t launch_ensemble_fast(const EnsArgs &a, double *sumsq_dev, cudaStream
     if (a.uni_scheme == SCHEME_NONE) e = k3 ? go(fast_mode::k_ensemble<SCHEME_NONE, 3>) : go(fast_mode::k_ensemble<SCHEME_NONE, 0>);
     else                             e = k3 ? go(fast_mode::k_ensemble<SCHEME_RUNTIME, 3>) : go(fast_mode::k_ensemble<SCHEME_RUNTIME, 0>);
     if (e != cudaSuccess) return e;
-    fast_mode::k_ens_reduce<<<(a.npar + 127) / 128, 128, 0, st>>>(a.partial, a.ntiles, a.npar, sumsq_dev);
+    if (mid) { if ((e = cudaEventRecord(mid, st)) != cudaSuccess) return e; }
+    if (p2p) fast_mode::k_ens_reduce_p2p<<<(a.npar + 127) / 128, 128, 0, st>>>(a.partial, a.ntiles, a.npar, sumsq_dev, *p2p);
+    else     fast_mode::k_ens_reduce<<<(a.npar + 127) / 128, 128, 0, st>>>(a.partial, a.ntiles, a.npar, sumsq_dev);
     return cudaGetLastError();
 }
 

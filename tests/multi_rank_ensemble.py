@@ -39,6 +39,7 @@ dist.broadcast(t, 0)
 uid = C.create_string_buffer(bytes(t.cpu().tolist()), 128)
 comm = C.c_void_p()
 check(L.semic_comm_init(C.byref(comm), uid, world, rank))
+fused = bool(L.semic_comm_p2p(comm, None, 0))
 lo, hi = driver.shard_bounds(NX, world, rank)
 cost = driver.run_particles(pop, names, np.ascontiguousarray(forc[:, :, lo:hi]), np.ascontiguousarray(vali[:, :, lo:hi]),
                             mask[lo:hi], init, NT, NLOOP, comm=comm)
@@ -55,6 +56,6 @@ dist.all_reduce(flags, op=dist.ReduceOp.MIN)
 if rank == 0:
     full = driver.run_particles(pop, names, forc, vali, mask, init, NT, NLOOP)
     err = max(abs(cost[k] - full[k]) / abs(full[k]) for k in full)
-    print(json.dumps({"world": world, "max_rel_err": err, "same_on_all_ranks": int(flags[0]) == 1, "allreduce_ms": ms.value,
+    print(json.dumps({"world": world, "max_rel_err": err, "same_on_all_ranks": int(flags[0]) == 1, "allreduce_ms": ms.value, "peer_memory": fused,
                       "finite": all(np.isfinite(v) for v in full.values())}))
 dist.destroy_process_group()
