@@ -911,7 +911,9 @@ __global__ void __launch_bounds__(WPC * 32, MINB) k_run(const __grid_constant__ 
     int stage = 0;
     uint32_t phase = 0;
 
-    for (long long tile = (long long)blockIdx.x * WPC + warp; tile < ntiles; tile += nwarps) {
+    // tile -> warp map interleaved over the CTAs: the ntiles % nwarps tiles of the last round land on ALL SMs (a few warps each)
+    // instead of filling the first SMs completely -- 3 % on a 2 Mi-point shard (18.45 tiles per warp)
+    for (long long tile = (long long)warp * gridDim.x + blockIdx.x; tile < ntiles; tile += nwarps) {
         const long long i = tile * kTile + lane;
         const bool valid = i < a.nx;
         const long long ii = valid ? i : 0;
@@ -1134,7 +1136,9 @@ __global__ void __launch_bounds__(WPC * 32, 1) k_run_lean(const __grid_constant_
     const uint32_t x_dst = FB + (uint32_t)x_row0 * kTile * (uint32_t)sizeof(double);       // stage rows 9 (stt) .. 14 (acc)
     const long long v_day = ntl * OBLK;                          // doubles per day of the external series
 
-    for (long long tile = (long long)blockIdx.x * WPC + warp; tile < ntiles; tile += nwarps) {
+    // tile -> warp map interleaved over the CTAs: the ntiles % nwarps tiles of the last round land on ALL SMs (a few warps each)
+    // instead of filling the first SMs completely -- 3 % on a 2 Mi-point shard (18.45 tiles per warp)
+    for (long long tile = (long long)warp * gridDim.x + blockIdx.x; tile < ntiles; tile += nwarps) {
         const double *ftile = a.forcing + tile * FBLK;
         int fd = a.f_day0 % a.f_nwin;                            // next forcing day to fetch and its address
         const double *fsrc = ftile + (long long)fd * f_day;
