@@ -426,6 +426,10 @@ struct Pt {
     double t2m, melt, melted_snow, melted_ice, refr, smb, acc, lhf, shf, lwu, subl, evap,
            smb_snow, smb_ice, runoff, qmr, amp;
     int mask;
+    // plain fast path: lwu, evap and runoff only matter in the final state (they feed nothing and are not daily output), so
+    // point_day leaves their ingredients here and finish_diagnostics() forms them on the day the state is stored
+    double aux_rr;          // refrozen_rain (runoff = (melt + rf) - refrozen_rain, :303; s.runoff holds rf, s.lwu holds ts^4,
+    bool aux_ice;           //  s.evap holds q of the last sub-step, aux_ice its ts < t0)
 };
 
 #define BND(x) (GENERIC && (B.x != 0))
@@ -516,7 +520,7 @@ DEVI void energy_substeps(double &ts, double &t2m, double &shf, double &lhf, dou
         if (nsub > 0) {
             shf = shf_c * d;
             lhf = lat * q;
-            lwu = sigm * t4;
+            lwu = t4;                                                          // ts^4: finish_diagnostics() scales it (:191)
             q_last = q;
             ice_last = __double2hiint(lat) == __double2hiint(kc[22]);          // the latent heat in use was cls (:421)
         }
@@ -571,6 +575,8 @@ DEVI unsigned point_day(Pt &s, const double *row, const long long T, const DevPa
                         const int eb_steps, const int do_mb, double &swd_out, const double *tab)
 {
     unsigned branch = 0;
+    bool any_over = false;              // fast plain path: a lane of the warp was clamped in the last sub-step (qmr != 0)
+    (void)any_over;
     const int mask = s.mask;
     const bool gate = (mask == 2) || (s.hsnow > 0.0);                 // :201,:209 (hsnow is constant over the sub-steps)
     if (WANT_BRANCH) { if (gate) branch |= SEMIC_B_GATE; }
@@ -615,7 +621,8 @@ DEVI unsigned point_day(Pt &s, const double *row, const long long T, const DevPa
             // amplifies the last bit of tmean by up to 1e5 (see diurnal_cycle_fast), so qmr and tmean are reproduced exactly
             // whenever the clamp excess itself is; days without a clamped lane (3 of 4) skip it
             qmr = 0.0;
-            if (__any_sync(__activemask(), over > 0.0)) qmr = fdiv_rn(__dmul_rn(over, P.ceff), P.tsticsub, P.inv_tsticsub);
+            any_over = __any_sync(__activemask(), over > 0.0);
+            if (any_over) qmr = fdiv_rn(__dmul_rn(over, P.ceff), P.tsticsub, P.inv_tsticsub);
 #endif
             if (WANT_BRANCH) { if (over > 0.0) branch |= SEMIC_B_CLAMP; }
             if (!BND(lhf)) {
@@ -626,7 +633,12 @@ DEVI unsigned point_day(Pt &s, const double *row, const long long T, const DevPa
 #else
                     subl = ice_last ? q_last * 1.0e-3 : 0.0;
 #endif
+#if SEMIC_STRICT
                     evap = ice_last ? 0.0 : q_last;
+#else
+                    evap = q_last;                                                 // finish_diagnostics(): ice_last ? 0 : q_last
+                    s.aux_ice = ice_last;
+#endif
                 }
             }
         }
@@ -644,7 +656,7 @@ DEVI unsigned point_day(Pt &s, const double *row, const long long T, const DevPa
         const double tmean = (ts - c_t0) + (fdiv(qmr, P.ceff) * P.tstic);          // :249
 #else
         double tmean = ts - kc[14];                                                // :249, unfused like the reference
-        if (__any_sync(__activemask(), qmr != 0.0))
+        if (GENERIC ? __any_sync(__activemask(), qmr != 0.0) : any_over)           // plain path: qmr != 0 only where the clamp fired
             tmean = __dadd_rn(tmean, __dmul_rn(fdiv_rn(qmr, P.ceff, P.inv_ceff), P.tstic));
 #endif
         double above, below;
@@ -714,7 +726,12 @@ DEVI unsigned point_day(Pt &s, const double *row, const long long T, const DevPa
 #endif
         }
 
+#if SEMIC_STRICT
         runoff = (melt + rf) - refrozen_rain;                                      // :302-303
+#else
+        if (GENERIC) runoff = (melt + rf) - refrozen_rain;
+        else { runoff = rf; s.aux_rr = refrozen_rain; }                            // finish_diagnostics()
+#endif
         if (!BND(acc)) acc = (sf - subl) + refr;                                   // :307
         if (!BND(smb)) smb_snow = ((sf - subl) - melted_snow) + refrozen_snow;     // :312
 
@@ -792,6 +809,23 @@ DEVI unsigned point_day(Pt &s, const double *row, const long long T, const DevPa
     s.smb = smb; s.acc = acc; s.lhf = lhf; s.shf = shf; s.lwu = lwu; s.subl = subl; s.evap = evap;
     s.smb_snow = smb_snow; s.smb_ice = smb_ice; s.runoff = runoff; s.qmr = qmr; s.amp = amp;
     return branch;
+}
+
+// lwu, evap, runoff of the plain fast path from the ingredients point_day left (see struct Pt); a no-op otherwise
+template <bool GENERIC>
+DEVI void finish_diagnostics(Pt &s, const int nsub)
+{
+#if !SEMIC_STRICT
+    if (!GENERIC) {
+        if (nsub > 0) {
+            s.lwu = kc[17] * s.lwu;                                                // :191
+            s.evap = s.aux_ice ? 0.0 : s.evap;                                     // :410-411,:427
+        }
+        s.runoff = (s.melt + s.runoff) - s.aux_rr;                                 // :302-303
+    }
+#else
+    (void)s; (void)nsub;
+#endif
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -1018,6 +1052,7 @@ __global__ void __launch_bounds__(WPC * 32, MINB) k_run(const __grid_constant__ 
 
         // final state of the tile: all 23 non-forcing fields, as after the reference's last call
         if (a.ndays > 0 && valid) {
+            if (GENERIC ? a.do_mb : 1) finish_diagnostics<GENERIC>(s, GENERIC ? a.eb_steps : a.P.n_ksub);
             double *S = a.slab + i;
             S[SEMIC_F_T2M * ld] = s.t2m;
             S[SEMIC_F_TSURF * ld] = s.tsurf;
@@ -1252,6 +1287,7 @@ __global__ void __launch_bounds__(WPC * 32, 1) k_run_lean(const __grid_constant_
                 }
             }
             if (d == dlast) {                   // final state: all 23 non-forcing fields, as after the reference's last call
+                if (EXT != 2) finish_diagnostics<false>(s, NK > 0 ? NK : a.P.n_ksub);
                 double *S = a.slab + i;
                 S[SEMIC_F_T2M * ld] = s.t2m;
                 S[SEMIC_F_TSURF * ld] = s.tsurf;
