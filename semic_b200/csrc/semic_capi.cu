@@ -101,6 +101,7 @@ static DevPar make_devpar(const semic_par *par)
     P.isba_new = par->tstic / P.isba_wcr * P.smax_m_smin;
     P.frz_rhow_clm = P.one_m_frz * rhow * clm;
     P.melt_per_kelvin = P.ceff_over_tstic * P.inv_rhow_clm;
+    { volatile double z = 0.0; P.rcrit_zero = par->rcrit * z; }
     P.inv_tsticsub = 1.0 / par->tsticsub;
     P.inv_ceff = 1.0 / par->ceff;
     P.n_ksub = par->n_ksub;

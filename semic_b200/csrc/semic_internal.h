@@ -50,6 +50,7 @@ struct DevPar {
     double inv_mcrit;        // 1/mcrit
     double isba_new;         // tstic/(w_crn/rhow)*(alb_smax-alb_smin)
     double frz_rhow_clm;     // (1-f_rz)*rhow*clm
+    double rcrit_zero;       // rcrit * (+0): the snow-refreezing term of a day without melt (keeps the sign of rcrit)
     double melt_per_kelvin;  // (ceff/tstic) * 1/(rhow*clm): melt or refreezing rate per kelvin of the diurnal integral (:254-266, :257-286)
     double inv_tsticsub;     // 1/tsticsub, 1/ceff: correctly rounded reciprocals for the exact quotients of :202, :249
     double inv_ceff;

@@ -687,13 +687,32 @@ DEVI unsigned point_day(Pt &s, const double *row, const long long T, const DevPa
         if (!BND(melt)) melt = fdiv(qmelt, P.rhow_clm);                            // :266
         const double hs_rate = fdiv(hsnow, P.tstic);
 #else
-        if (!BND(melt)) melt = above * c_mask;
         // IEEE quotient: when all snow melts, hsnow - (hsnow/tstic)*tstic decides between "bare" and a
         // one-ulp ghost snow layer (which keeps the :201 gate on over land); keep the reference's rounding
         // (one Newton refinement of hsnow*(1/tstic) is the correctly rounded quotient up to ~2^-50 odds: 3 instructions
         //  instead of the ~15 of the general IEEE division routine)
         const double hs_q = hsnow * P.inv_tstic;
         const double hs_rate = fma(fma(-hs_q, P.tstic, hsnow), P.inv_tstic, hs_q);
+        // A whole warp below the melting range (tmean + amp < 0 on every lane: 3 days of 4): above = +0, hence melt,
+        // melted_snow, melted_ice = +0 and the snow-refreezing term is rcrit*(+0).  The short form below produces the bits of
+        // the general statements (x - (+0) = x, min(+0, hs_rate) = +0 for hs_rate >= +0), it only skips them.
+        const bool cold_warp = !GENERIC && __all_sync(__activemask(), dbr == 0 && __double2hiint(hsnow) >= 0);
+#endif
+        double refrozen_rain = 0.0, refrozen_snow = 0.0;                           // Q5: defined as 0 under bnd%refr
+#if !SEMIC_STRICT
+        if (cold_warp) {
+            melt = 0.0; melted_snow = 0.0; melted_ice = 0.0;                       // :266-280
+            refr = fabs(below) * c_mask;                                           // :286
+            refrozen_rain = P.rcrit * dmin1(hs_rate, dmin1(refr, rf));             // :287,:293
+            refrozen_snow = P.rcrit_zero;                                          // :289-294: rcrit*min(hs_rate, min(., +0))
+            refr = refrozen_rain + refrozen_snow;                                  // :295
+            qmr = -(refr * P.frz_rhow_clm);                                        // :298
+            if (GENERIC) runoff = (melt + rf) - refrozen_rain;
+            else { runoff = rf; s.aux_rr = refrozen_rain; }
+            acc = (sf - subl) + refr;                                              // :307
+            smb_snow = (sf - subl) + refrozen_snow;                                // :312 with melted_snow = +0
+        } else {
+        if (!BND(melt)) melt = above * c_mask;
 #endif
         melted_snow = dmin1(melt, hs_rate);                                         // :269
         melted_ice  = melt - melted_snow;                                          // :270
@@ -702,7 +721,6 @@ DEVI unsigned point_day(Pt &s, const double *row, const long long T, const DevPa
             melt = melted_snow + melted_ice;                                       // x + 0 == x: the land/ocean branch of :277
         }
 
-        double refrozen_rain = 0.0, refrozen_snow = 0.0;                           // Q5: defined as 0 under bnd%refr
         if (!BND(refr)) {                                                          // :283-299
 #if SEMIC_STRICT
             refr = fdiv(qcold, P.rhow_clm);                                        // :286
@@ -734,6 +752,9 @@ DEVI unsigned point_day(Pt &s, const double *row, const long long T, const DevPa
 #endif
         if (!BND(acc)) acc = (sf - subl) + refr;                                   // :307
         if (!BND(smb)) smb_snow = ((sf - subl) - melted_snow) + refrozen_snow;     // :312
+#if !SEMIC_STRICT
+        }   // !cold_warp
+#endif
 
 #if SEMIC_STRICT
         if (mask == 0) hsnow = 0.0;                                                // :315-320
@@ -744,21 +765,38 @@ DEVI unsigned point_day(Pt &s, const double *row, const long long T, const DevPa
             hsnow = ((hs_new > 0.0) & (mask != 0)) ? hs_new : 0.0;                 // :315-320 with one select
         }
 #endif
+#if SEMIC_STRICT
         const double snow_to_ice = dmax1(0.0, hsnow - c_hsmax);                     // :323
         hsnow = hsnow - snow_to_ice;                                               // :324
-#if SEMIC_STRICT
         const double s2i_rate = fdiv(snow_to_ice, P.tstic);
         smb_ice = (s2i_rate - melted_ice) + refrozen_rain;                         // :325
         hice = hice + (smb_ice * P.tstic);                                         // :326
-#else
-        const double s2i_rate = snow_to_ice * P.inv_tstic;
-        smb_ice = (s2i_rate - melted_ice) + refrozen_rain;
-        hice = fma(smb_ice, P.tstic, hice);
-#endif
         if (!BND(smb)) {                                                           // :329-335
             if (mask == 2) smb = (smb_snow + smb_ice) - s2i_rate;
             else           smb = smb_snow + dmax1(0.0, smb_ice - s2i_rate);
         }
+#else
+        // no lane of the warp above hsmax (the usual case): snow_to_ice = +0 and :324-:334 lose their s2i terms exactly
+        double snow_to_ice = 0.0;
+        const double over5 = hsnow - c_hsmax;                                      // :323
+        if (__any_sync(__activemask(), over5 > 0.0)) {
+            snow_to_ice = dmax1(0.0, over5);
+            hsnow = hsnow - snow_to_ice;                                           // :324
+            const double s2i_rate = snow_to_ice * P.inv_tstic;
+            smb_ice = (s2i_rate - melted_ice) + refrozen_rain;                     // :325
+            if (!BND(smb)) {                                                       // :329-335
+                if (mask == 2) smb = (smb_snow + smb_ice) - s2i_rate;
+                else           smb = smb_snow + dmax1(0.0, smb_ice - s2i_rate);
+            }
+        } else {
+            smb_ice = (0.0 - melted_ice) + refrozen_rain;
+            if (!BND(smb)) {
+                if (mask == 2) smb = smb_snow + smb_ice;
+                else           smb = smb_snow + dmax1(0.0, smb_ice);
+            }
+        }
+        hice = fma(smb_ice, P.tstic, hice);                                        // :326
+#endif
         if (WANT_BRANCH) { if (melt > 0.0) branch |= SEMIC_B_MELT_POS; }
         if (WANT_BRANCH) { if (hsnow == 0.0) branch |= SEMIC_B_HSNOW_ZERO; }
         if (WANT_BRANCH) { if (snow_to_ice > 0.0) branch |= SEMIC_B_SNOW2ICE; }
