@@ -472,7 +472,62 @@ DEVI void energy_substeps(double &ts, double &t2m, double &shf, double &lhf, dou
 }
 #else
 // Fast arithmetic.  This translation unit is compiled with -fmad=false: every fused operation below is written as
-// fma(), so all instantiations (unroll factors, compile-time n_ksub, bitmap or not) produce the same bits.
+// fma(), so all instantiations (unroll factors, compile-time n_ksub, bitmap or not, one or two points per lane) produce
+// the same bits.
+// One sub-step of the plain path (no boundary flag but tsurf/alb of EXT2) on the values of one point: SubK holds the day's
+// constants, SubV what changes from sub-step to sub-step.  shf, lhf, lwu of the LAST sub-step are formed after the loop
+// (substep_diag) from d, q, the latent heat and ts^4.
+struct SubK { double shf_c, lat_a, lat_b, sp, radq, cg; bool gate; };
+struct SubV { double ts, t2m, ts_raw, lat_next, na, b, d, q, lat, t4; };
+
+template <bool ALLG>
+DEVI void substep_init(SubV &v, const double ts, const double t2m)
+{
+    // ts < t0 as a signed 64-bit integer compare of the bit patterns: identical to the floating-point
+    // compares for every non-NaN ts (t0 > 0), and they run on the ALU pipe in the shadow of the FP64 pipe, which is the
+    // busy one (DSETP costs it two cycles per warp, profiles/r01_summary.md section 4).  One compare per sub-step serves
+    // both decisions: the next sub-step's ts < t0 (:415) is !(ts_raw >= t0) whether or not the clamp fires.
+    // The selects that depend on it (latent heat, the ei/ew constants) are made right at the compare, for the NEXT sub-step,
+    // and carried as values: the compiler otherwise re-issues the compare at every use.
+    const bool ice0 = __double_as_longlong(ts) < __double_as_longlong(kc[14]);
+    v.ts = ts; v.t2m = t2m; v.ts_raw = ts;
+    v.lat_next = ice0 ? kc[22] : kc[23];
+    v.na = (ALLG || ice0) ? kc[24] : kc[25];
+    v.b = (ALLG || ice0) ? kc[19] : kc[21];
+    v.d = 0.0; v.q = 0.0; v.lat = 0.0; v.t4 = 0.0;
+}
+
+template <bool ALLG, bool EXT2>
+DEVI void substep_plain(SubV &v, const SubK &K, const double c, const semic_bnd &B, const double *tab)
+{
+    const double t0 = kc[14], sigm = kc[17];
+    const long long t0_bits = __double_as_longlong(t0);
+    v.lat = v.lat_next;                                                        // :415 decided on the tsurf this sub-step starts from
+    v.q = latent_q_ab(v.ts, K.lat_a, K.lat_b, K.sp, v.na, v.b, tab);           // :179-185
+    v.d = v.ts - v.t2m;                                                        // :173
+    const double t2 = v.ts * v.ts;
+    v.t4 = t2 * t2;                                                            // :191
+    const double sl = fma(K.shf_c, v.d, v.lat * v.q);                          // shf + lhf, shared by :194 and :210
+    const double qsb = fma(-sigm, v.t4, K.radq) - sl;                          // :194
+    v.t2m = fma(sl, K.cg, v.t2m);                                              // :209-211 (Q1: forcing t2m is mutated)
+    if (!(EXT2 && B.tsurf != 0)) {                                             // :198 (external tsurf stays as given)
+        v.ts_raw = fma(qsb, c, v.ts);                                          // :199
+        // warm = !(tsurf < t0) of the next sub-step; tsurf = t0 if gated and warm (:201-204; ts_raw == t0: the same value)
+        if (ALLG) clamp_and_latent(v.ts_raw, t0_bits, t0, K.gate, kc[22], kc[23], v.ts, v.lat_next);
+        else      clamp_and_latent_ab(v.ts_raw, t0_bits, t0, K.gate, kc[22], kc[23], kc[24], kc[25], kc[19], kc[21], v.ts,
+                                      v.lat_next, v.na, v.b);
+    }
+}
+
+DEVI void substep_diag(const SubV &v, const SubK &K, double &shf, double &lhf, double &lwu, double &q_last, bool &ice_last)
+{
+    shf = K.shf_c * v.d;
+    lhf = v.lat * v.q;
+    lwu = v.t4;                                                                // ts^4: finish_diagnostics() scales it (:191)
+    q_last = v.q;
+    ice_last = __double2hiint(v.lat) == __double2hiint(kc[22]);                // the latent heat in use was cls (:421)
+}
+
 // ALLG: every lane of the warp is gated (mask == 2 or snow covered) with ts <= t0; a compile-time true removes selects.
 template <bool GENERIC, bool ALLG, int UNR, bool EXT2 = false>
 DEVI void energy_substeps(double &ts, double &t2m, double &shf, double &lhf, double &subl, double &evap, double &lwu,
@@ -490,40 +545,13 @@ DEVI void energy_substeps(double &ts, double &t2m, double &shf, double &lhf, dou
     const long long t0_bits = __double_as_longlong(t0);
     if (!GENERIC) {
         // the diagnostics shf, lhf, lwu of the last sub-step are formed after the loop from d, q, latent heat and ts^4
-        double d = 0.0, q = 0.0, lat = 0.0, t4 = 0.0;
-        // ts < t0 as a signed 64-bit integer compare of the bit patterns: identical to the floating-point
-        // compares for every non-NaN ts (t0 > 0), and they run on the ALU pipe in the shadow of the FP64 pipe, which is the
-        // busy one (DSETP costs it two cycles per warp, profiles/r01_summary.md section 4).  One compare per sub-step serves
-        // both decisions: the next sub-step's ts < t0 (:415) is !(ts_raw >= t0) whether or not the clamp fires.
-        // The selects that depend on it (latent heat, the ei/ew constants) are made right at the compare, for the NEXT sub-step,
-        // and carried as values: the compiler otherwise re-issues the compare at every use.
-        const bool ice0 = __double_as_longlong(ts) < t0_bits;
-        double lat_next = ice0 ? kc[22] : kc[23];
-        double na = (ALLG || ice0) ? kc[24] : kc[25], b = (ALLG || ice0) ? kc[19] : kc[21];
+        const SubK K = {shf_c, lat_a, lat_b, sp, radq, cg, gate};
+        SubV v;
+        substep_init<ALLG>(v, ts, t2m);
 #pragma unroll UNR
-        for (int k = 0; k < nsub; ++k) {
-            lat = lat_next;                                                    // :415 decided on the tsurf this sub-step starts from
-            q = latent_q_ab(ts, lat_a, lat_b, sp, na, b, tab);                 // :179-185
-            d = ts - t2m;                                                      // :173
-            const double t2 = ts * ts;
-            t4 = t2 * t2;                                                      // :191
-            const double sl = fma(shf_c, d, lat * q);                          // shf + lhf, shared by :194 and :210
-            const double qsb = fma(-sigm, t4, radq) - sl;                      // :194
-            t2m = fma(sl, cg, t2m);                                            // :209-211 (Q1: forcing t2m is mutated)
-            if (!BNDX(tsurf)) {                                                // :198 (external tsurf stays as given)
-                ts_raw = fma(qsb, c, ts);                                      // :199
-                // warm = !(tsurf < t0) of the next sub-step; tsurf = t0 if gated and warm (:201-204; ts_raw == t0: the same value)
-                if (ALLG) clamp_and_latent(ts_raw, t0_bits, t0, gate, kc[22], kc[23], ts, lat_next);
-                else      clamp_and_latent_ab(ts_raw, t0_bits, t0, gate, kc[22], kc[23], kc[24], kc[25], kc[19], kc[21], ts, lat_next, na, b);
-            }
-        }
-        if (nsub > 0) {
-            shf = shf_c * d;
-            lhf = lat * q;
-            lwu = t4;                                                          // ts^4: finish_diagnostics() scales it (:191)
-            q_last = q;
-            ice_last = __double2hiint(lat) == __double2hiint(kc[22]);          // the latent heat in use was cls (:421)
-        }
+        for (int k = 0; k < nsub; ++k) substep_plain<ALLG, EXT2>(v, K, c, B, tab);
+        ts = v.ts; t2m = v.t2m; ts_raw = v.ts_raw;
+        if (nsub > 0) substep_diag(v, K, shf, lhf, lwu, q_last, ice_last);
     } else {
         // all boundary flags; the same fused forms as above wherever the flag set allows, so that a run whose flags are
         // a subset of {tsurf, alb} gives the same bits here and in the EXT2 instantiation of the plain path
@@ -566,52 +594,117 @@ DEVI void energy_substeps(double &ts, double &t2m, double &shf, double &lhf, dou
 #endif
 
 
+// A day is three pieces, so that a lane can run the sub-steps of two points side by side (k_run_lean2): day_head reads the
+// forcing and forms the day's constants, day_substeps runs n_ksub x energy_balance, day_tail takes the last sub-step's
+// excess into mass_balance.  DayCtx carries the values from piece to piece; point_day is the three in a row.
+struct DayCtx {
+    double ts, t2m, shf, lhf, subl, evap, lwu;          // running values of energy_balance
+    double shf_c, lhf_c, rad, qq, sp;                   // day constants
+    double q_last, over;                                // q and clamp excess of the last sub-step
+    bool gate, ice_last;
+    int nsub;
+};
+
+template <bool GENERIC, int NK>
+DEVI void day_head(const Pt &s, const double *row, const long long T, const DevPar &P, const int eb_steps, double &swd_out,
+                   DayCtx &c)
+{
+    c.gate = (s.mask == 2) || (s.hsnow > 0.0);                        // :201,:209 (hsnow is constant over the sub-steps)
+    c.ts = s.tsurf;
+    c.t2m = row[SEMIC_V_T2M * T];
+    c.shf = s.shf; c.lhf = s.lhf; c.subl = s.subl; c.evap = s.evap; c.lwu = s.lwu;
+    const double wind = row[SEMIC_V_WIND * T], rhoa = row[SEMIC_V_RHOA * T];
+    const double swd = row[SEMIC_V_SWD * T];
+    swd_out = swd;
+    // exact hoists: literal left-to-right prefixes of :387, :420/:427 and :194
+    c.shf_c  = (P.csh_cap * rhoa) * wind;
+    c.lhf_c  = (P.clh * wind) * rhoa;
+#if SEMIC_STRICT
+    c.rad    = ((1.0 - s.alb) * swd) + row[SEMIC_V_LWD * T];
+#else
+    c.rad    = fma(1.0 - s.alb, swd, row[SEMIC_V_LWD * T]);
+#endif
+    c.qq = row[SEMIC_V_QQ * T];
+    c.sp = row[SEMIC_V_SP * T];
+    c.q_last = 0.0; c.over = 0.0;
+    c.ice_last = false;
+    c.nsub = GENERIC ? eb_steps : (NK > 0 ? NK : P.n_ksub);           // NK: n_ksub known at compile time
+}
+
+// ---------------- energy_balance x nsub (:149-151, :158-214) ----------------
+template <bool GENERIC, int UNR, bool EXT2>
+DEVI void day_substeps(DayCtx &c, const double qmr_res, const DevPar &P, const semic_bnd &B, const double *tab)
+{
+    // gated points never exceed t0 (:201-204), which removes the ei/ew constant selects (see latent_q); taken when
+    // every active lane of the warp is gated, e.g. the interior of an ice sheet
+    const bool allg = !GENERIC && !SEMIC_STRICT && __all_sync(__activemask(), c.gate && c.ts <= c_t0);
+    if (allg)
+        energy_substeps<GENERIC, true, UNR, EXT2>(c.ts, c.t2m, c.shf, c.lhf, c.subl, c.evap, c.lwu, c.q_last, c.over, c.ice_last,
+                                                  c.shf_c, c.lhf_c, c.rad, c.qq, c.sp, qmr_res, c.gate, c.nsub, P, B, tab);
+    else
+        energy_substeps<GENERIC, false, UNR, EXT2>(c.ts, c.t2m, c.shf, c.lhf, c.subl, c.evap, c.lwu, c.q_last, c.over, c.ice_last,
+                                                   c.shf_c, c.lhf_c, c.rad, c.qq, c.sp, qmr_res, c.gate, c.nsub, P, B, tab);
+}
+
+#if !SEMIC_STRICT
+// The plain sub-step loop for TWO points of one lane side by side (k_run_lean2).  One point's sub-steps are a single
+// dependency chain (tsurf -> exp -> q -> qsb -> tsurf), so a warp waits on the FP64 pipe's latency between most instructions;
+// two independent chains in one instruction stream fill those slots.  The arithmetic per point is substep_plain's, hence the
+// bits are those of energy_substeps.  ALLG as there, for the points of both tiles.
+template <bool ALLG, int UNR>
+DEVI void energy_substeps2(DayCtx &a, DayCtx &b, const double qmr_res_a, const double qmr_res_b, const DevPar &P,
+                           const semic_bnd &B, const double *tab)
+{
+    const double t0 = kc[14], c = P.sub_over_ceff;
+    const bool ga = ALLG ? true : a.gate, gb = ALLG ? true : b.gate;
+    const SubK Ka = {a.shf_c, a.lhf_c * kc[15], a.lhf_c * a.qq, a.sp, a.rad - qmr_res_a, ga ? c : 0.0, ga};
+    const SubK Kb = {b.shf_c, b.lhf_c * kc[15], b.lhf_c * b.qq, b.sp, b.rad - qmr_res_b, gb ? c : 0.0, gb};
+    SubV va, vb;
+    substep_init<ALLG>(va, a.ts, a.t2m);
+    substep_init<ALLG>(vb, b.ts, b.t2m);
+    const int nsub = a.nsub;
+#pragma unroll UNR
+    for (int k = 0; k < nsub; ++k) {
+        substep_plain<ALLG, false>(va, Ka, c, B, tab);
+        substep_plain<ALLG, false>(vb, Kb, c, B, tab);
+    }
+    a.ts = va.ts; a.t2m = va.t2m;
+    b.ts = vb.ts; b.t2m = vb.t2m;
+    if (nsub > 0) {
+        substep_diag(va, Ka, a.shf, a.lhf, a.lwu, a.q_last, a.ice_last);
+        substep_diag(vb, Kb, b.shf, b.lhf, b.lwu, b.q_last, b.ice_last);
+        a.over = (ga && va.ts_raw > t0) ? va.ts_raw - t0 : 0.0;                // only the last sub-step's excess survives (:197, Q2)
+        b.over = (gb && vb.ts_raw > t0) ? vb.ts_raw - t0 : 0.0;
+    }
+}
+
+template <int UNR>
+DEVI void day_substeps2(DayCtx &a, DayCtx &b, const double qmr_res_a, const double qmr_res_b, const DevPar &P,
+                        const semic_bnd &B, const double *tab)
+{
+    const bool allg = __all_sync(__activemask(), a.gate && a.ts <= c_t0 && b.gate && b.ts <= c_t0);
+    if (allg) energy_substeps2<true, UNR>(a, b, qmr_res_a, qmr_res_b, P, B, tab);
+    else      energy_substeps2<false, UNR>(a, b, qmr_res_a, qmr_res_b, P, B, tab);
+}
+#endif
+
 // `row` points at this point's column of the day's forcing (a shared-memory stage in k_run, global
 // memory in k_ensemble): variable v is row[v*T].  Values are read where they are first needed (LDS
-// is cheap, registers across the sub-step loop are not); `swd_out` returns the day's shortwave for
-// the swnet diagnostic.
-template <int SCHEME, bool GENERIC, bool WANT_BRANCH, int UNR = 2, int NK = 0, bool EXT2 = false>
-DEVI unsigned point_day(Pt &s, const double *row, const long long T, const DevPar &P, const semic_bnd &B,
-                        const int eb_steps, const int do_mb, double &swd_out, const double *tab)
+// is cheap, registers across the sub-step loop are not).
+template <int SCHEME, bool GENERIC, bool WANT_BRANCH, bool EXT2>
+DEVI unsigned day_tail(Pt &s, const double *row, const long long T, const DevPar &P, const semic_bnd &B, const int do_mb,
+                       DayCtx &c, const double *tab)
 {
     unsigned branch = 0;
     bool any_over = false;              // fast plain path: a lane of the warp was clamped in the last sub-step (qmr != 0)
     (void)any_over;
     const int mask = s.mask;
-    const bool gate = (mask == 2) || (s.hsnow > 0.0);                 // :201,:209 (hsnow is constant over the sub-steps)
-    if (WANT_BRANCH) { if (gate) branch |= SEMIC_B_GATE; }
-
-    double ts = s.tsurf;
-    double t2m = row[SEMIC_V_T2M * T];
-    double shf = s.shf, lhf = s.lhf, subl = s.subl, evap = s.evap, lwu = s.lwu, qmr = s.qmr;
-
-    // ---------------- energy_balance x eb_steps (:149-151, :158-214) ----------------
+    if (WANT_BRANCH) { if (c.gate) branch |= SEMIC_B_GATE; }
+    double ts = c.ts, t2m = c.t2m, shf = c.shf, lhf = c.lhf, subl = c.subl, evap = c.evap, lwu = c.lwu, qmr = s.qmr;
     {
-        const double wind = row[SEMIC_V_WIND * T], rhoa = row[SEMIC_V_RHOA * T];
-        const double swd = row[SEMIC_V_SWD * T];
-        swd_out = swd;
-        // exact hoists: literal left-to-right prefixes of :387, :420/:427 and :194
-        const double shf_c  = (P.csh_cap * rhoa) * wind;
-        const double lhf_c  = (P.clh * wind) * rhoa;
-#if SEMIC_STRICT
-        const double rad    = ((1.0 - s.alb) * swd) + row[SEMIC_V_LWD * T];
-#else
-        const double rad    = fma(1.0 - s.alb, swd, row[SEMIC_V_LWD * T]);
-#endif
-        const double qq = row[SEMIC_V_QQ * T], sp = row[SEMIC_V_SP * T];
-        double q_last = 0.0, over = 0.0;
-        bool ice_last = false;
-        const int nsub = GENERIC ? eb_steps : (NK > 0 ? NK : P.n_ksub);        // NK: n_ksub known at compile time
-        const bool any = nsub > 0;
-        // gated points never exceed t0 (:201-204), which removes the ei/ew constant selects (see latent_q); taken when
-        // every active lane of the warp is gated, e.g. the interior of an ice sheet
-        const bool allg = !GENERIC && !SEMIC_STRICT && __all_sync(__activemask(), gate && ts <= c_t0);
-        if (allg)
-            energy_substeps<GENERIC, true, UNR, EXT2>(ts, t2m, shf, lhf, subl, evap, lwu, q_last, over, ice_last, shf_c, lhf_c, rad,
-                                                qq, sp, s.qmr_res, gate, nsub, P, B, tab);
-        else
-            energy_substeps<GENERIC, false, UNR, EXT2>(ts, t2m, shf, lhf, subl, evap, lwu, q_last, over, ice_last, shf_c, lhf_c, rad,
-                                                 qq, sp, s.qmr_res, gate, nsub, P, B, tab);
+        const double q_last = c.q_last, over = c.over;
+        const bool ice_last = c.ice_last;
+        const bool any = c.nsub > 0;
         if (any) {
             // only the last sub-step's qmr survives (:197, Q2)
 #if SEMIC_STRICT
@@ -847,6 +940,17 @@ DEVI unsigned point_day(Pt &s, const double *row, const long long T, const DevPa
     s.smb = smb; s.acc = acc; s.lhf = lhf; s.shf = shf; s.lwu = lwu; s.subl = subl; s.evap = evap;
     s.smb_snow = smb_snow; s.smb_ice = smb_ice; s.runoff = runoff; s.qmr = qmr; s.amp = amp;
     return branch;
+}
+
+// one point, one day; `swd_out` returns the day's shortwave for the swnet diagnostic
+template <int SCHEME, bool GENERIC, bool WANT_BRANCH, int UNR = 2, int NK = 0, bool EXT2 = false>
+DEVI unsigned point_day(Pt &s, const double *row, const long long T, const DevPar &P, const semic_bnd &B,
+                        const int eb_steps, const int do_mb, double &swd_out, const double *tab)
+{
+    DayCtx c;
+    day_head<GENERIC, NK>(s, row, T, P, eb_steps, swd_out, c);
+    day_substeps<GENERIC, UNR, EXT2>(c, s.qmr_res, P, B, tab);
+    return day_tail<SCHEME, GENERIC, WANT_BRANCH, EXT2>(s, row, T, P, B, do_mb, c, tab);
 }
 
 // lwu, evap, runoff of the plain fast path from the ingredients point_day left (see struct Pt); a no-op otherwise
@@ -1160,6 +1264,63 @@ struct LeanSmem {
     static constexpr size_t bytes = ring_bytes + bar_bytes + kExpTab * sizeof(double);      // rings, barriers, exp table
 };
 
+// the 23 non-forcing fields of one point into its slab column (the state after the reference's last call)
+DEVI void store_state(double *S, const long long ld, const Pt &s)
+{
+    S[SEMIC_F_T2M * ld] = s.t2m;
+    S[SEMIC_F_TSURF * ld] = s.tsurf;
+    S[SEMIC_F_HSNOW * ld] = s.hsnow;
+    S[SEMIC_F_HICE * ld] = s.hice;
+    S[SEMIC_F_ALB * ld] = s.alb;
+    S[SEMIC_F_ALB_SNOW * ld] = s.alb_snow;
+    S[SEMIC_F_MELT * ld] = s.melt;
+    S[SEMIC_F_MELTED_SNOW * ld] = s.melted_snow;
+    S[SEMIC_F_MELTED_ICE * ld] = s.melted_ice;
+    S[SEMIC_F_REFR * ld] = s.refr;
+    S[SEMIC_F_SMB * ld] = s.smb;
+    S[SEMIC_F_ACC * ld] = s.acc;
+    S[SEMIC_F_LHF * ld] = s.lhf;
+    S[SEMIC_F_SHF * ld] = s.shf;
+    S[SEMIC_F_LWU * ld] = s.lwu;
+    S[SEMIC_F_SUBL * ld] = s.subl;
+    S[SEMIC_F_EVAP * ld] = s.evap;
+    S[SEMIC_F_SMB_SNOW * ld] = s.smb_snow;
+    S[SEMIC_F_SMB_ICE * ld] = s.smb_ice;
+    S[SEMIC_F_RUNOFF * ld] = s.runoff;
+    S[SEMIC_F_QMR * ld] = s.qmr;
+    S[SEMIC_F_QMR_RES * ld] = s.qmr_res;
+    S[SEMIC_F_AMP * ld] = s.amp;
+}
+// the carried prognostics of a plain run (surface_physics.f90:56-90); the rest of the state is rewritten daily
+DEVI void load_carried(Pt &s, const double *S, const long long ld, const int mask)
+{
+    s.mask = mask;
+    s.tsurf    = S[SEMIC_F_TSURF * ld];
+    s.hsnow    = S[SEMIC_F_HSNOW * ld];
+    s.hice     = S[SEMIC_F_HICE * ld];
+    s.alb      = S[SEMIC_F_ALB * ld];
+    s.alb_snow = S[SEMIC_F_ALB_SNOW * ld];
+    s.qmr_res  = S[SEMIC_F_QMR_RES * ld];
+    s.melt = s.melted_snow = s.melted_ice = s.refr = s.smb = s.acc = 0.0;
+    s.lhf = s.shf = s.lwu = s.subl = s.evap = s.smb_snow = s.smb_ice = 0.0;
+    s.runoff = s.qmr = s.amp = 0.0;
+    s.t2m = 0.0;
+    s.aux_rr = 0.0;
+    s.aux_ice = false;
+}
+// the 8 daily rows of one point (example.f90:117-122)
+DEVI void store_daily(double *oday, const Pt &s, const double swd)
+{
+    oday[SEMIC_O_STT * kTile]   = s.tsurf;
+    oday[SEMIC_O_ALB * kTile]   = s.alb;
+    oday[SEMIC_O_SWNET * kTile] = swd * (1.0 - s.alb);
+    oday[SEMIC_O_SMB * kTile]   = s.smb;
+    oday[SEMIC_O_MELT * kTile]  = s.melt;
+    oday[SEMIC_O_ACC * kTile]   = s.acc;
+    oday[SEMIC_O_SHF * kTile]   = s.shf;
+    oday[SEMIC_O_LHF * kTile]   = s.lhf;
+}
+
 template <int SCHEME, int WPC, int UNR, int NK, bool AVG = false, int EXT = 0>
 __global__ void __launch_bounds__(WPC * 32, 1) k_run_lean(const __grid_constant__ RunArgs a)
 {
@@ -1294,14 +1455,7 @@ __global__ void __launch_bounds__(WPC * 32, 1) k_run_lean(const __grid_constant_
             else          point_day<SCHEME, false, false, UNR, NK, EXT == 1>(s, row, kTile, a.P, a.B, 0, 1, swd, tab);
             if (d >= ostart) {                                   // example.f90:117-122
                 if (!AVG) {
-                    oday[SEMIC_O_STT * kTile]   = s.tsurf;
-                    oday[SEMIC_O_ALB * kTile]   = s.alb;
-                    oday[SEMIC_O_SWNET * kTile] = swd * (1.0 - s.alb);
-                    oday[SEMIC_O_SMB * kTile]   = s.smb;
-                    oday[SEMIC_O_MELT * kTile]  = s.melt;
-                    oday[SEMIC_O_ACC * kTile]   = s.acc;
-                    oday[SEMIC_O_SHF * kTile]   = s.shf;
-                    oday[SEMIC_O_LHF * kTile]   = s.lhf;
+                    store_daily(oday, s, swd);
                 } else {
                     avg[SEMIC_O_STT]   += s.tsurf;               // field_average 'step' (:614)
                     avg[SEMIC_O_ALB]   += s.alb;
@@ -1326,30 +1480,7 @@ __global__ void __launch_bounds__(WPC * 32, 1) k_run_lean(const __grid_constant_
             }
             if (d == dlast) {                   // final state: all 23 non-forcing fields, as after the reference's last call
                 if (EXT != 2) finish_diagnostics<false>(s, NK > 0 ? NK : a.P.n_ksub);
-                double *S = a.slab + i;
-                S[SEMIC_F_T2M * ld] = s.t2m;
-                S[SEMIC_F_TSURF * ld] = s.tsurf;
-                S[SEMIC_F_HSNOW * ld] = s.hsnow;
-                S[SEMIC_F_HICE * ld] = s.hice;
-                S[SEMIC_F_ALB * ld] = s.alb;
-                S[SEMIC_F_ALB_SNOW * ld] = s.alb_snow;
-                S[SEMIC_F_MELT * ld] = s.melt;
-                S[SEMIC_F_MELTED_SNOW * ld] = s.melted_snow;
-                S[SEMIC_F_MELTED_ICE * ld] = s.melted_ice;
-                S[SEMIC_F_REFR * ld] = s.refr;
-                S[SEMIC_F_SMB * ld] = s.smb;
-                S[SEMIC_F_ACC * ld] = s.acc;
-                S[SEMIC_F_LHF * ld] = s.lhf;
-                S[SEMIC_F_SHF * ld] = s.shf;
-                S[SEMIC_F_LWU * ld] = s.lwu;
-                S[SEMIC_F_SUBL * ld] = s.subl;
-                S[SEMIC_F_EVAP * ld] = s.evap;
-                S[SEMIC_F_SMB_SNOW * ld] = s.smb_snow;
-                S[SEMIC_F_SMB_ICE * ld] = s.smb_ice;
-                S[SEMIC_F_RUNOFF * ld] = s.runoff;
-                S[SEMIC_F_QMR * ld] = s.qmr;
-                S[SEMIC_F_QMR_RES * ld] = s.qmr_res;
-                S[SEMIC_F_AMP * ld] = s.amp;
+                store_state(a.slab + i, ld, s);
             }
             // every lane has consumed its column of the stage (the loaded values fed the arithmetic above): refill it
             __syncwarp();
@@ -1369,6 +1500,135 @@ __global__ void __launch_bounds__(WPC * 32, 1) k_run_lean(const __grid_constant_
         }
     }
 }
+
+#if !SEMIC_STRICT
+// k_run_lean with TWO adjacent tiles per warp: lane l carries points 64*pair + l and 64*pair + 32 + l and runs their
+// sub-steps side by side (energy_substeps2).  For large n_ksub the kernel is bound by the FP64 pipe and by the latency of
+// the one dependency chain a point's sub-steps form; two chains per lane keep the pipe busier than more warps of one chain
+// do (tools/wpc_sweep.sh).  The two tiles' forcing is contiguous in the tiled layout, so a stage is ONE bulk copy of 4608 B.
+// Plain runs with daily rows only (no period means, no external rows); results are bit-identical to k_run_lean's.
+template <int WPC>
+struct Lean2Smem {
+    static constexpr int STAGES = 2;
+    static constexpr size_t stage_bytes = 2 * (size_t)kForcingRows * kTile * sizeof(double);   // 4608 B
+    static constexpr size_t ring_bytes = stage_bytes * STAGES * WPC;
+    static constexpr size_t bar_bytes = (size_t)WPC * STAGES * sizeof(uint64_t);
+    static constexpr size_t bytes = ring_bytes + bar_bytes + kExpTab * sizeof(double);
+};
+
+template <int SCHEME, int WPC, int UNR, int NK>
+__global__ void __launch_bounds__(WPC * 32, 1) k_run_lean2(const __grid_constant__ RunArgs a)
+{
+    using SM = Lean2Smem<WPC>;
+    constexpr int NST = SM::STAGES;
+    constexpr uint32_t SB = (uint32_t)SM::stage_bytes;
+    constexpr uint32_t FB = (uint32_t)(kForcingRows * kTile * sizeof(double));   // forcing bytes per tile-day
+    constexpr int FBLK = kForcingRows * kTile;                   // doubles per tile-day of forcing
+    constexpr int OBLK = SEMIC_NOUT * kTile;                     // doubles per tile-day of output
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
+    const int lane = threadIdx.x & 31;
+    const uint32_t smem_u = smem_u32(smem_raw);
+    const uint32_t ring_u = smem_u + (uint32_t)(warp * NST) * SB;
+    const uint32_t bar_u = smem_u + (uint32_t)SM::ring_bytes + (uint32_t)(warp * NST) * 8u;
+    const double *ring = reinterpret_cast<const double *>(smem_raw + (size_t)(warp * NST) * SB) + lane;
+    double *tab = reinterpret_cast<double *>(smem_raw + SM::ring_bytes + SM::bar_bytes);
+
+    if (lane == 0) {
+        for (int s = 0; s < NST; ++s) mbar_init(bar_u + 8u * s, 1);
+        mbar_fence_init();
+    }
+    for (int j = threadIdx.x; j < kExpTab; j += WPC * 32) tab[j] = g_exp2_tab[j];
+    __syncthreads();
+
+    const long long ld = a.ld;
+    const long long ntl = a.sld / kTile;                         // tiles per series row
+    const long long ntiles = ((long long)a.nx + kTile - 1) / kTile;
+    const long long npairs = (ntiles + 1) / 2;
+    const long long nwarps = (long long)gridDim.x * WPC;
+    const long long f_day = ntl * FBLK;                          // doubles per forcing day
+    const long long o_day = ntl * OBLK;
+    const int ndays = a.ndays;
+    __builtin_assume(a.P.n_ksub >= 1);
+    int ostart = (a.out != nullptr) ? a.out_start : ndays;       // first day that is written
+    asm volatile("" : "+r"(ostart));
+    uint32_t stage = 0, phase = 0;
+
+    for (long long pair = (long long)warp * gridDim.x + blockIdx.x; pair < npairs; pair += nwarps) {
+        const long long tile = 2 * pair;
+        const bool two = tile + 1 < ntiles;                      // the last pair of an odd tile count is one tile
+        const uint32_t bytes = two ? 2u * FB : FB;
+        const double *ftile = a.forcing + tile * FBLK;
+        int fd = a.f_day0 % a.f_nwin;                            // next forcing day to fetch and its address
+        const double *fsrc = ftile + (long long)fd * f_day;
+        int d_issue = 0;
+        {
+            uint32_t s = stage;
+            const int npre = ndays < NST ? ndays : NST;
+            for (; d_issue < npre; ++d_issue) {
+                if (elect_one()) {
+                    mbar_expect_tx(bar_u + 8u * s, bytes);
+                    tma_load_1d(ring_u + s * SB, fsrc, bytes, bar_u + 8u * s);
+                }
+                fsrc += f_day;
+                if (++fd == a.f_nwin) { fd = 0; fsrc = ftile; }
+                if (++s == NST) s = 0;
+            }
+        }
+
+        const long long ia = tile * kTile + lane;
+        const long long ib = two ? ia + kTile : ia;              // a single tile: the second point repeats the first, unstored
+        int dlast_a = (ia < a.nx) ? ndays - 1 : -1;              // the day whose full state this lane stores
+        int dlast_b = (two && ib < a.nx) ? ndays - 1 : -1;
+        asm volatile("" : "+r"(dlast_a), "+r"(dlast_b));
+        Pt sa, sb;
+        load_carried(sa, a.slab + ia, ld, a.mask[ia]);
+        load_carried(sb, a.slab + ib, ld, a.mask[ib]);
+        double *oday = a.out + tile * OBLK + lane;
+        int oslot = 0;
+
+        for (int d = 0; d < ndays; ++d) {
+            mbar_wait(bar_u + 8u * stage, phase);
+            const double *row_a = ring + (size_t)stage * (SB / sizeof(double));
+            const double *row_b = two ? row_a + FBLK : row_a;
+            double swd_a, swd_b;
+            DayCtx ca, cb;
+            day_head<false, NK>(sa, row_a, kTile, a.P, 0, swd_a, ca);
+            day_head<false, NK>(sb, row_b, kTile, a.P, 0, swd_b, cb);
+            day_substeps2<UNR>(ca, cb, sa.qmr_res, sb.qmr_res, a.P, a.B, tab);
+            day_tail<SCHEME, false, false, false>(sa, row_a, kTile, a.P, a.B, 1, ca, tab);
+            if (d >= ostart) store_daily(oday, sa, swd_a);       // example.f90:117-122
+            if (d == dlast_a) {
+                finish_diagnostics<false>(sa, NK > 0 ? NK : a.P.n_ksub);
+                store_state(a.slab + ia, ld, sa);
+            }
+            day_tail<SCHEME, false, false, false>(sb, row_b, kTile, a.P, a.B, 1, cb, tab);
+            if (d >= ostart) {
+                if (two) store_daily(oday + OBLK, sb, swd_b);
+                oday += o_day;
+                if (++oslot == a.o_nring) { oslot = 0; oday -= (long long)a.o_nring * o_day; }
+            }
+            if (d == dlast_b) {
+                finish_diagnostics<false>(sb, NK > 0 ? NK : a.P.n_ksub);
+                store_state(a.slab + ib, ld, sb);
+            }
+            // every lane has consumed its columns of the stage: refill it
+            __syncwarp();
+            if (d_issue < ndays) {
+                if (elect_one()) {
+                    fence_proxy_async();       // generic-proxy reads of the stage (above) before the async-proxy overwrite
+                    mbar_expect_tx(bar_u + 8u * stage, bytes);
+                    tma_load_1d(ring_u + stage * SB, fsrc, bytes, bar_u + 8u * stage);
+                }
+                ++d_issue;
+                fsrc += f_day;
+                if (++fd == a.f_nwin) { fd = 0; fsrc = ftile; }
+            }
+            if (++stage == NST) { stage = 0; phase ^= 1u; }
+        }
+    }
+}
+#endif
 
 // ------------------------------------------------------------------------------------------------
 // ensemble misfit (optimize/run_particles.f90:104-178 + utils.f90:23-42), config 5
