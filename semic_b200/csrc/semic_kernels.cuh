@@ -472,8 +472,7 @@ DEVI void energy_substeps(double &ts, double &t2m, double &shf, double &lhf, dou
 }
 #else
 // Fast arithmetic.  This translation unit is compiled with -fmad=false: every fused operation below is written as
-// fma(), so all instantiations (unroll factors, compile-time n_ksub, bitmap or not, one or two points per lane) produce
-// the same bits.
+// fma(), so all instantiations (unroll factors, compile-time n_ksub, bitmap or not) produce the same bits.
 // One sub-step of the plain path (no boundary flag but tsurf/alb of EXT2) on the values of one point: SubK holds the day's
 // constants, SubV what changes from sub-step to sub-step.  shf, lhf, lwu of the LAST sub-step are formed after the loop
 // (substep_diag) from d, q, the latent heat and ts^4.
@@ -594,9 +593,9 @@ DEVI void energy_substeps(double &ts, double &t2m, double &shf, double &lhf, dou
 #endif
 
 
-// A day is three pieces, so that a lane can run the sub-steps of two points side by side (k_run_lean2): day_head reads the
-// forcing and forms the day's constants, day_substeps runs n_ksub x energy_balance, day_tail takes the last sub-step's
-// excess into mass_balance.  DayCtx carries the values from piece to piece; point_day is the three in a row.
+// A day is three pieces: day_head reads the forcing and forms the day's constants, day_substeps runs n_ksub x
+// energy_balance, day_tail takes the last sub-step's excess into mass_balance.  DayCtx carries the values from piece to
+// piece; point_day is the three in a row.
 struct DayCtx {
     double ts, t2m, shf, lhf, subl, evap, lwu;          // running values of energy_balance
     double shf_c, lhf_c, rad, qq, sp;                   // day constants
@@ -645,48 +644,6 @@ DEVI void day_substeps(DayCtx &c, const double qmr_res, const DevPar &P, const s
         energy_substeps<GENERIC, false, UNR, EXT2>(c.ts, c.t2m, c.shf, c.lhf, c.subl, c.evap, c.lwu, c.q_last, c.over, c.ice_last,
                                                    c.shf_c, c.lhf_c, c.rad, c.qq, c.sp, qmr_res, c.gate, c.nsub, P, B, tab);
 }
-
-#if !SEMIC_STRICT
-// The plain sub-step loop for TWO points of one lane side by side (k_run_lean2).  One point's sub-steps are a single
-// dependency chain (tsurf -> exp -> q -> qsb -> tsurf), so a warp waits on the FP64 pipe's latency between most instructions;
-// two independent chains in one instruction stream fill those slots.  The arithmetic per point is substep_plain's, hence the
-// bits are those of energy_substeps.  ALLG as there, for the points of both tiles.
-template <bool ALLG, int UNR>
-DEVI void energy_substeps2(DayCtx &a, DayCtx &b, const double qmr_res_a, const double qmr_res_b, const DevPar &P,
-                           const semic_bnd &B, const double *tab)
-{
-    const double t0 = kc[14], c = P.sub_over_ceff;
-    const bool ga = ALLG ? true : a.gate, gb = ALLG ? true : b.gate;
-    const SubK Ka = {a.shf_c, a.lhf_c * kc[15], a.lhf_c * a.qq, a.sp, a.rad - qmr_res_a, ga ? c : 0.0, ga};
-    const SubK Kb = {b.shf_c, b.lhf_c * kc[15], b.lhf_c * b.qq, b.sp, b.rad - qmr_res_b, gb ? c : 0.0, gb};
-    SubV va, vb;
-    substep_init<ALLG>(va, a.ts, a.t2m);
-    substep_init<ALLG>(vb, b.ts, b.t2m);
-    const int nsub = a.nsub;
-#pragma unroll UNR
-    for (int k = 0; k < nsub; ++k) {
-        substep_plain<ALLG, false>(va, Ka, c, B, tab);
-        substep_plain<ALLG, false>(vb, Kb, c, B, tab);
-    }
-    a.ts = va.ts; a.t2m = va.t2m;
-    b.ts = vb.ts; b.t2m = vb.t2m;
-    if (nsub > 0) {
-        substep_diag(va, Ka, a.shf, a.lhf, a.lwu, a.q_last, a.ice_last);
-        substep_diag(vb, Kb, b.shf, b.lhf, b.lwu, b.q_last, b.ice_last);
-        a.over = (ga && va.ts_raw > t0) ? va.ts_raw - t0 : 0.0;                // only the last sub-step's excess survives (:197, Q2)
-        b.over = (gb && vb.ts_raw > t0) ? vb.ts_raw - t0 : 0.0;
-    }
-}
-
-template <int UNR>
-DEVI void day_substeps2(DayCtx &a, DayCtx &b, const double qmr_res_a, const double qmr_res_b, const DevPar &P,
-                        const semic_bnd &B, const double *tab)
-{
-    const bool allg = __all_sync(__activemask(), a.gate && a.ts <= c_t0 && b.gate && b.ts <= c_t0);
-    if (allg) energy_substeps2<true, UNR>(a, b, qmr_res_a, qmr_res_b, P, B, tab);
-    else      energy_substeps2<false, UNR>(a, b, qmr_res_a, qmr_res_b, P, B, tab);
-}
-#endif
 
 // `row` points at this point's column of the day's forcing (a shared-memory stage in k_run, global
 // memory in k_ensemble): variable v is row[v*T].  Values are read where they are first needed (LDS
@@ -1291,23 +1248,6 @@ DEVI void store_state(double *S, const long long ld, const Pt &s)
     S[SEMIC_F_QMR_RES * ld] = s.qmr_res;
     S[SEMIC_F_AMP * ld] = s.amp;
 }
-// the carried prognostics of a plain run (surface_physics.f90:56-90); the rest of the state is rewritten daily
-DEVI void load_carried(Pt &s, const double *S, const long long ld, const int mask)
-{
-    s.mask = mask;
-    s.tsurf    = S[SEMIC_F_TSURF * ld];
-    s.hsnow    = S[SEMIC_F_HSNOW * ld];
-    s.hice     = S[SEMIC_F_HICE * ld];
-    s.alb      = S[SEMIC_F_ALB * ld];
-    s.alb_snow = S[SEMIC_F_ALB_SNOW * ld];
-    s.qmr_res  = S[SEMIC_F_QMR_RES * ld];
-    s.melt = s.melted_snow = s.melted_ice = s.refr = s.smb = s.acc = 0.0;
-    s.lhf = s.shf = s.lwu = s.subl = s.evap = s.smb_snow = s.smb_ice = 0.0;
-    s.runoff = s.qmr = s.amp = 0.0;
-    s.t2m = 0.0;
-    s.aux_rr = 0.0;
-    s.aux_ice = false;
-}
 // the 8 daily rows of one point (example.f90:117-122)
 DEVI void store_daily(double *oday, const Pt &s, const double swd)
 {
@@ -1500,135 +1440,6 @@ __global__ void __launch_bounds__(WPC * 32, 1) k_run_lean(const __grid_constant_
         }
     }
 }
-
-#if !SEMIC_STRICT
-// k_run_lean with TWO adjacent tiles per warp: lane l carries points 64*pair + l and 64*pair + 32 + l and runs their
-// sub-steps side by side (energy_substeps2).  For large n_ksub the kernel is bound by the FP64 pipe and by the latency of
-// the one dependency chain a point's sub-steps form; two chains per lane keep the pipe busier than more warps of one chain
-// do (tools/wpc_sweep.sh).  The two tiles' forcing is contiguous in the tiled layout, so a stage is ONE bulk copy of 4608 B.
-// Plain runs with daily rows only (no period means, no external rows); results are bit-identical to k_run_lean's.
-template <int WPC>
-struct Lean2Smem {
-    static constexpr int STAGES = 2;
-    static constexpr size_t stage_bytes = 2 * (size_t)kForcingRows * kTile * sizeof(double);   // 4608 B
-    static constexpr size_t ring_bytes = stage_bytes * STAGES * WPC;
-    static constexpr size_t bar_bytes = (size_t)WPC * STAGES * sizeof(uint64_t);
-    static constexpr size_t bytes = ring_bytes + bar_bytes + kExpTab * sizeof(double);
-};
-
-template <int SCHEME, int WPC, int UNR, int NK>
-__global__ void __launch_bounds__(WPC * 32, 1) k_run_lean2(const __grid_constant__ RunArgs a)
-{
-    using SM = Lean2Smem<WPC>;
-    constexpr int NST = SM::STAGES;
-    constexpr uint32_t SB = (uint32_t)SM::stage_bytes;
-    constexpr uint32_t FB = (uint32_t)(kForcingRows * kTile * sizeof(double));   // forcing bytes per tile-day
-    constexpr int FBLK = kForcingRows * kTile;                   // doubles per tile-day of forcing
-    constexpr int OBLK = SEMIC_NOUT * kTile;                     // doubles per tile-day of output
-    extern __shared__ __align__(128) unsigned char smem_raw[];
-    const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
-    const int lane = threadIdx.x & 31;
-    const uint32_t smem_u = smem_u32(smem_raw);
-    const uint32_t ring_u = smem_u + (uint32_t)(warp * NST) * SB;
-    const uint32_t bar_u = smem_u + (uint32_t)SM::ring_bytes + (uint32_t)(warp * NST) * 8u;
-    const double *ring = reinterpret_cast<const double *>(smem_raw + (size_t)(warp * NST) * SB) + lane;
-    double *tab = reinterpret_cast<double *>(smem_raw + SM::ring_bytes + SM::bar_bytes);
-
-    if (lane == 0) {
-        for (int s = 0; s < NST; ++s) mbar_init(bar_u + 8u * s, 1);
-        mbar_fence_init();
-    }
-    for (int j = threadIdx.x; j < kExpTab; j += WPC * 32) tab[j] = g_exp2_tab[j];
-    __syncthreads();
-
-    const long long ld = a.ld;
-    const long long ntl = a.sld / kTile;                         // tiles per series row
-    const long long ntiles = ((long long)a.nx + kTile - 1) / kTile;
-    const long long npairs = (ntiles + 1) / 2;
-    const long long nwarps = (long long)gridDim.x * WPC;
-    const long long f_day = ntl * FBLK;                          // doubles per forcing day
-    const long long o_day = ntl * OBLK;
-    const int ndays = a.ndays;
-    __builtin_assume(a.P.n_ksub >= 1);
-    int ostart = (a.out != nullptr) ? a.out_start : ndays;       // first day that is written
-    asm volatile("" : "+r"(ostart));
-    uint32_t stage = 0, phase = 0;
-
-    for (long long pair = (long long)warp * gridDim.x + blockIdx.x; pair < npairs; pair += nwarps) {
-        const long long tile = 2 * pair;
-        const bool two = tile + 1 < ntiles;                      // the last pair of an odd tile count is one tile
-        const uint32_t bytes = two ? 2u * FB : FB;
-        const double *ftile = a.forcing + tile * FBLK;
-        int fd = a.f_day0 % a.f_nwin;                            // next forcing day to fetch and its address
-        const double *fsrc = ftile + (long long)fd * f_day;
-        int d_issue = 0;
-        {
-            uint32_t s = stage;
-            const int npre = ndays < NST ? ndays : NST;
-            for (; d_issue < npre; ++d_issue) {
-                if (elect_one()) {
-                    mbar_expect_tx(bar_u + 8u * s, bytes);
-                    tma_load_1d(ring_u + s * SB, fsrc, bytes, bar_u + 8u * s);
-                }
-                fsrc += f_day;
-                if (++fd == a.f_nwin) { fd = 0; fsrc = ftile; }
-                if (++s == NST) s = 0;
-            }
-        }
-
-        const long long ia = tile * kTile + lane;
-        const long long ib = two ? ia + kTile : ia;              // a single tile: the second point repeats the first, unstored
-        int dlast_a = (ia < a.nx) ? ndays - 1 : -1;              // the day whose full state this lane stores
-        int dlast_b = (two && ib < a.nx) ? ndays - 1 : -1;
-        asm volatile("" : "+r"(dlast_a), "+r"(dlast_b));
-        Pt sa, sb;
-        load_carried(sa, a.slab + ia, ld, a.mask[ia]);
-        load_carried(sb, a.slab + ib, ld, a.mask[ib]);
-        double *oday = a.out + tile * OBLK + lane;
-        int oslot = 0;
-
-        for (int d = 0; d < ndays; ++d) {
-            mbar_wait(bar_u + 8u * stage, phase);
-            const double *row_a = ring + (size_t)stage * (SB / sizeof(double));
-            const double *row_b = two ? row_a + FBLK : row_a;
-            double swd_a, swd_b;
-            DayCtx ca, cb;
-            day_head<false, NK>(sa, row_a, kTile, a.P, 0, swd_a, ca);
-            day_head<false, NK>(sb, row_b, kTile, a.P, 0, swd_b, cb);
-            day_substeps2<UNR>(ca, cb, sa.qmr_res, sb.qmr_res, a.P, a.B, tab);
-            day_tail<SCHEME, false, false, false>(sa, row_a, kTile, a.P, a.B, 1, ca, tab);
-            if (d >= ostart) store_daily(oday, sa, swd_a);       // example.f90:117-122
-            if (d == dlast_a) {
-                finish_diagnostics<false>(sa, NK > 0 ? NK : a.P.n_ksub);
-                store_state(a.slab + ia, ld, sa);
-            }
-            day_tail<SCHEME, false, false, false>(sb, row_b, kTile, a.P, a.B, 1, cb, tab);
-            if (d >= ostart) {
-                if (two) store_daily(oday + OBLK, sb, swd_b);
-                oday += o_day;
-                if (++oslot == a.o_nring) { oslot = 0; oday -= (long long)a.o_nring * o_day; }
-            }
-            if (d == dlast_b) {
-                finish_diagnostics<false>(sb, NK > 0 ? NK : a.P.n_ksub);
-                store_state(a.slab + ib, ld, sb);
-            }
-            // every lane has consumed its columns of the stage: refill it
-            __syncwarp();
-            if (d_issue < ndays) {
-                if (elect_one()) {
-                    fence_proxy_async();       // generic-proxy reads of the stage (above) before the async-proxy overwrite
-                    mbar_expect_tx(bar_u + 8u * stage, bytes);
-                    tma_load_1d(ring_u + stage * SB, fsrc, bytes, bar_u + 8u * stage);
-                }
-                ++d_issue;
-                fsrc += f_day;
-                if (++fd == a.f_nwin) { fd = 0; fsrc = ftile; }
-            }
-            if (++stage == NST) { stage = 0; phase ^= 1u; }
-        }
-    }
-}
-#endif
 
 // ------------------------------------------------------------------------------------------------
 // ensemble misfit (optimize/run_particles.f90:104-178 + utils.f90:23-42), config 5

@@ -61,40 +61,6 @@ static cudaError_t launch_lean_one(const RunArgs &a, cudaStream_t st)
     return cudaGetLastError();
 }
 
-// k_run_lean2: two adjacent tiles per warp (n_ksub large: FP64-pipe bound)
-template <int SCHEME, int WPC, int UNR, int NK>
-static cudaError_t launch_lean2_one(const RunArgs &a, cudaStream_t st)
-{
-    auto kern = k_run_lean2<SCHEME, WPC, UNR, NK>;
-    constexpr size_t smem = Lean2Smem<WPC>::bytes;
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return e;
-    int dev = 0, nsm = 0;
-    if ((e = cudaGetDevice(&dev)) != cudaSuccess) return e;
-    if ((e = cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev)) != cudaSuccess) return e;
-    const long long ntiles = ((long long)a.nx + kTile - 1) / kTile;
-    const long long npairs = (ntiles + 1) / 2;
-    long long grid = nsm;                       // persistent: one CTA per SM, every warp walks its tile pairs
-    const long long need = (npairs + WPC - 1) / WPC;
-    if (grid > need) grid = need;
-    if (grid < 1) return cudaSuccess;
-    kern<<<(unsigned)grid, WPC * 32, smem, st>>>(a);
-    return cudaGetLastError();
-}
-
-template <int WPC, int UNR, int NK>
-static cudaError_t launch_lean2_nk(const RunArgs &a, cudaStream_t st)
-{
-    switch (a.P.scheme) {
-        case SCHEME_NONE:   return launch_lean2_one<SCHEME_NONE, WPC, UNR, NK>(a, st);
-        case SCHEME_SLATER: return launch_lean2_one<SCHEME_SLATER, WPC, UNR, NK>(a, st);
-        case SCHEME_DENBY:  return launch_lean2_one<SCHEME_DENBY, WPC, UNR, NK>(a, st);
-        case SCHEME_ISBA:   return launch_lean2_one<SCHEME_ISBA, WPC, UNR, NK>(a, st);
-        case SCHEME_ALEX:   return launch_lean2_one<SCHEME_ALEX, WPC, UNR, NK>(a, st);
-        default:            return launch_lean2_one<SCHEME_UNKNOWN, WPC, UNR, NK>(a, st);
-    }
-}
-
 template <int WPC, int UNR, int NK, bool AVG, int EXT = 0>
 static cudaError_t launch_lean_nk(const RunArgs &a, cudaStream_t st)
 {
@@ -133,9 +99,6 @@ static cudaError_t launch_lean(const RunArgs &a, cudaStream_t st, int ext)
     if (a.P.n_ksub == 24) {                                                   // BASELINE configs[1]: trip count known, unrolled by 4
         const char *w = getenv("SEMIC_WPC");                                  // experiment knob (tools/ab.py): warps per CTA
         const int wpc = w ? atoi(w) : 24;
-        const char *two = getenv("SEMIC_LEAN2");                              // experiment knob: two tiles per warp
-        if (two && atoi(two) == 16) return launch_lean2_nk<16, 2, 24>(a, st);
-        if (two && atoi(two) == 12) return launch_lean2_nk<12, 2, 24>(a, st);
         if (wpc == 16) return launch_lean_nk<16, 4, 24, false>(a, st);
         if (wpc == 28) return launch_lean_nk<28, 4, 24, false>(a, st);
         if (wpc == 32) return launch_lean_nk<32, 4, 24, false>(a, st);
