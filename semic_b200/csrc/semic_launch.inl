@@ -53,15 +53,18 @@ static cudaError_t launch_lean_one(const RunArgs &a, cudaStream_t st)
     if ((e = cudaGetDevice(&dev)) != cudaSuccess) return e;
     if ((e = cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev)) != cudaSuccess) return e;
     const long long ntiles = ((long long)a.nx + kTile - 1) / kTile;
-    // persistent: one CTA per SM, every warp walks its tiles.  A grid of fewer tiles than warp slots is SPREAD over all SMs
-    // (tile t on CTA t % grid), not packed into full CTAs: a tile's run is one dependent chain, and the fewer warps share a
-    // scheduler the faster each chain goes (60 000 points x 365 days, n_ksub = 24: 1.93 ms spread, 2.63 ms packed into 79 CTAs;
-    // SEMIC_SPREAD=0 packs, for A/B timing)
+    // persistent: one CTA per SM, every warp walks its tiles.  A small grid is SPREAD over all SMs (tile t on CTA t % grid)
+    // instead of packed into full CTAs when that leaves every scheduler at least one warp short of full: a tile's run is one
+    // dependent chain, and the fewer warps share a scheduler the faster each chain goes (60 000 points x 365 days, n_ksub = 24:
+    // 1.92 ms spread, 2.63 ms packed into 79 CTAs).  Between WPC - 4 and WPC tiles per SM the fullest scheduler is full either
+    // way and packing is as fast (n_ksub = 24) or faster (n_ksub = 3: 0.84 against 0.90 ms at 100 000 points).
+    // SEMIC_SPREAD=0 always packs, SEMIC_SPREAD=1 always spreads (A/B timing).
     long long grid = nsm;
-    long long need = ntiles;
+    long long need = (ntiles + WPC - 1) / WPC;
     {
         const char *sp = getenv("SEMIC_SPREAD");
-        if (sp && atoi(sp) == 0) need = (ntiles + WPC - 1) / WPC;
+        const bool spread = sp ? atoi(sp) != 0 : ntiles <= (long long)(WPC - 4) * nsm;
+        if (spread) need = ntiles;
     }
     if (grid > need) grid = need;
     if (grid < 1) return cudaSuccess;
