@@ -384,7 +384,8 @@ contains
         ntc = -1.0_c_double
         if (present(nt)) ntc = nt
         call check(semic_average_c(ave%handle, now%handle, trim(step)//c_null_char, ntc), 'surface_physics_average')
-        if (trim(step) .eq. "end") call check(semic_state_download(ave%handle, int(z'FFFFFFFF', c_int64_t)), 'surface_physics_average')
+        if (trim(step) .eq. "end") &
+            call check(semic_state_download(ave%handle, int(z'FFFFFFFF', c_int64_t)), 'surface_physics_average')
     end subroutine
 
     !> surface_physics.f90:633-677
