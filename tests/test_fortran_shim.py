@@ -197,3 +197,187 @@ def test_bind_c_interfaces_have_the_argument_counts_of_the_prototypes():
         assert nargs == proto[m.group(2)], "%s: %d dummy arguments, the prototype has %d" % (m.group(2), nargs, proto[m.group(2)])
         checked += 1
     assert checked >= 15
+
+
+# ---- implicit none: every identifier of every procedure is a dummy, a local, a module-level name, a keyword or an intrinsic ----
+_KEYWORDS = set("""if then else elseif end endif do while call return stop error exit cycle select case default where elsewhere
+ subroutine function module contains use only implicit none interface procedure type integer real double precision character
+ logical complex intent in out inout optional pointer contiguous dimension target allocatable parameter value import bind
+ c name result pure elemental recursive write print read open close unit file status iostat fmt len kind intrinsic
+ and or not eq ne lt le gt ge true false eqv neqv nullify allocate deallocate stat associate save public private""".split())
+_INTRINSICS = set("""trim adjustl adjustr int real dble merge size present associated len_trim achar char ichar iachar min max abs
+ epsilon null c_f_pointer c_loc c_associated c_funloc ieee_value ieee_quiet_nan shape reshape transfer huge tiny sqrt exp
+ c_int c_double c_char c_ptr c_null_char c_null_ptr c_int64_t c_long c_size_t c_float c_bool iso_c_binding ieee_arithmetic
+ lbound ubound index scan verify repeat any all count sum product maxval minval mod nint floor ceiling sign""".split())
+_DECL = re.compile(r"^(integer|real|double precision|character|logical|type\s*\(|class\s*\()", re.I)
+_PROC = re.compile(r"(?:(?:pure|elemental|recursive|integer\s*\([^)]*\)|integer|type\s*\([^)]*\)|real\s*\([^)]*\)|double precision|logical)\s+)*"
+                   r"(subroutine|function)\s+(\w+)\s*(\(([^)]*)\))?")
+
+
+def _idents(s):
+    s = re.sub(r"z'[0-9a-fA-F]+'", " ", s)                                    # BOZ literals
+    s = re.sub(r"'[^']*'|\"[^\"]*\"", " ", s)                                  # strings
+    s = re.sub(r"(?<![\w])\d+\.?\d*([ed][+-]?\d+)?(_\w+)?", " ", s, flags=re.I)  # numbers with a kind suffix
+    s = re.sub(r"%\s*\w+", " ", s)                                             # components
+    s = re.sub(r"\b\w+\s*=(?!=)", lambda m: m.group(0) if not re.match(r".*[(,]\s*$", s[:m.start()]) else " ", s)   # keyword arguments
+    s = re.sub(r"\.\w+\.", " ", s)                                             # .and. .eq. ...
+    return [t.lower() for t in re.findall(r"[A-Za-z_]\w*", s)]
+
+
+def _decl_names(s):
+    return [re.sub(r"(\(.*|=>.*|=.*)", "", part).strip().lower() for part in re.split(r",(?![^()]*\))", s.split("::", 1)[1])]
+
+
+def _undeclared(lines):
+    """list of (procedure, identifier, statement) for identifiers that nothing declares"""
+    modnames, procs, cur, in_iface = set(), [], None, 0
+    for s in lines:
+        low = s.lower()
+        if re.match(r"interface\b", low):
+            in_iface += 1
+            m = re.match(r"interface\s+(\w+)", low)
+            if m:
+                modnames.add(m.group(1))
+            continue
+        if re.match(r"end\s*interface", low):
+            in_iface -= 1
+            continue
+        m = _PROC.match(low)
+        if m:
+            modnames.add(m.group(2))
+            if not in_iface:
+                cur = dict(name=m.group(2), args=[a.strip() for a in (m.group(4) or "").split(",") if a.strip()], body=[], res=None)
+                r = re.search(r"result\s*\(\s*(\w+)\s*\)", low)
+                if r:
+                    cur["res"] = r.group(1)
+                procs.append(cur)
+            continue
+        if re.match(r"end\s*(subroutine|function)", low):
+            if not in_iface:
+                cur = None
+            continue
+        if in_iface:
+            continue
+        if cur is None:
+            if _DECL.match(low) and "::" in low:
+                modnames.update(_decl_names(s))
+            m = re.match(r"type\s*(,[^:]*)?(::)?\s*(\w+)$", low)
+            if m:
+                modnames.add(m.group(3))
+        else:
+            cur["body"].append(s)
+    bad = []
+    for p in procs:
+        local = set(p["args"]) | {p["name"]}
+        if p["res"]:
+            local.add(p["res"])
+        for s in p["body"]:
+            if _DECL.match(s.lower()) and "::" in s:
+                local.update(_decl_names(s))
+        for s in p["body"]:
+            if _DECL.match(s.lower()) and "::" in s:
+                toks = _idents(s.split("::", 1)[0])
+                for part in re.split(r",(?![^()]*\))", s.split("::", 1)[1]):
+                    toks += _idents(re.sub(r"^[^=(]*", "", part))
+            else:
+                toks = _idents(s)
+            bad += [(p["name"], t, s) for t in toks if not (t in _KEYWORDS or t in _INTRINSICS or t in local or t in modnames)]
+        bad += [(p["name"], a, "dummy argument without a declaration") for a in p["args"]
+                if not any(_DECL.match(s.lower()) and "::" in s and a in _decl_names(s) for s in p["body"])]
+    return bad, len(procs)
+
+
+def test_every_identifier_is_declared():
+    """the module is `implicit none`: an undeclared name is a compile error"""
+    bad, nproc = _undeclared(_logical_lines())
+    assert nproc >= 20 and bad == []
+
+
+def test_the_identifier_check_sees_a_seeded_mistake():
+    lines = [s.replace("integer :: q, k", "integer :: q") for s in _logical_lines()]      # par_to_c loses the declaration of k
+    bad, _ = _undeclared(lines)
+    assert {(p, t) for p, t, _ in bad} >= {("par_to_c", "k"), ("par_from_c", "k")}
+    lines = [s.replace("call par_to_c(par, pc)", "call par_to_c(par, pcc)") for s in _logical_lines()]
+    assert any(t == "pcc" for _, t, _ in _undeclared(lines)[0])
+
+
+def _call_sites(stmt, name):
+    """argument counts of every reference `name(...)` in a statement (balanced parentheses, top-level commas)"""
+    s = re.sub(r"'[^']*'|\"[^\"]*\"", "''", stmt)
+    out = []
+    for m in re.finditer(r"(?<![\w%%])%s\s*\(" % re.escape(name), s, re.I):
+        depth, i, commas, empty = 1, m.end(), 0, True
+        while i < len(s) and depth:
+            ch = s[i]
+            if ch in "([":
+                depth += 1
+            elif ch in ")]":
+                depth -= 1
+            elif ch == "," and depth == 1:
+                commas += 1
+            if depth and not ch.isspace():
+                empty = False
+            i += 1
+        out.append(0 if empty else commas + 1)
+    return out
+
+
+def test_references_pass_as_many_arguments_as_the_procedures_take():
+    lines = _logical_lines()
+    sig, optional, in_proc = {}, set(), None
+    for s in lines:
+        low = s.lower()
+        m = _PROC.match(low)
+        if m:
+            in_proc = m.group(2)
+            sig[in_proc] = len([a for a in (m.group(4) or "").split(",") if a.strip()])
+        elif in_proc and "optional" in low.split("::")[0]:
+            optional.add(in_proc)
+    checked = 0
+    for s in lines:
+        low = s.lower()
+        if _PROC.match(low) or re.match(r"(end\b|module procedure)", low):
+            continue
+        for name, n in sig.items():
+            if name in optional or name not in low:
+                continue
+            for got in _call_sites(s, name):
+                assert got == n, "%s takes %d arguments, %d given in: %s" % (name, n, got, s[:120])
+                checked += 1
+    assert checked >= 40
+
+
+def test_elemental_procedures_only_reference_pure_interfaces_and_generics_name_real_procedures():
+    lines = _logical_lines()
+    pure, defined, iface_funcs = set(), set(), set()
+    in_iface = 0
+    for s in lines:
+        low = s.lower()
+        if re.match(r"interface\b", low):
+            in_iface += 1
+        elif re.match(r"end\s*interface", low):
+            in_iface -= 1
+        m = _PROC.match(low)
+        if m:
+            (iface_funcs if in_iface else defined).add(m.group(2))
+            if re.match(r"(pure|elemental)\b", low):
+                pure.add(m.group(2))
+    for s in lines:
+        m = re.match(r"module procedure\s+(.*)$", s.lower())
+        if m:
+            for name in m.group(1).split(","):
+                assert name.strip() in defined, name
+    cur = None
+    for s in lines:
+        low = s.lower()
+        m = _PROC.match(low)
+        if m:
+            cur = m.group(2) if re.match(r"elemental\b", low) else None
+            continue
+        if re.match(r"end\s*(subroutine|function)", low):
+            cur = None
+        if cur:
+            for f in iface_funcs | defined:
+                if f != cur and _call_sites(s, f):
+                    assert f in pure, "%s (elemental) references %s, which is not pure" % (cur, f)
+            assert not re.match(r"(call check|error stop|stop|write|print)\b", low), "%s: %s" % (cur, s)
