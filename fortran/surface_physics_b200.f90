@@ -21,7 +21,6 @@
 module surface_physics
 
     use, intrinsic :: iso_c_binding
-    use, intrinsic :: ieee_arithmetic, only: ieee_value, ieee_quiet_nan
     implicit none
 
     integer, parameter:: dp=kind(0.d0)
@@ -167,17 +166,18 @@ module surface_physics
         type(c_ptr) function semic_last_error() bind(C, name="semic_last_error")
             import :: c_ptr
         end function
-        ! the three public elementals, evaluated by the library on the device over n values (include/semic_b200.h).
-        ! Declared PURE (they have no side effect visible to Fortran; the result arrays are reached through C pointers
-        ! passed by value), so that the module can keep the reference's ELEMENTAL interfaces on top of them.
-        pure integer(c_int) function semic_shf_c(ts, ta, wind, rhoa, csh, cap, shf, n) bind(C, name="semic_sensible_heat_flux")
+        ! the three public elementals, evaluated by the library on the device (include/semic_b200.h): over n values for the
+        ! rank-1 specifics, one value returned as the function RESULT for the elemental specifics.  Only the latter are
+        ! declared PURE: every dummy is passed by VALUE and nothing reaches Fortran through a pointer, so they are pure in
+        ! the sense of the standard and an optimising compiler has nothing to assume wrongly.
+        integer(c_int) function semic_shf_c(ts, ta, wind, rhoa, csh, cap, shf, n) bind(C, name="semic_sensible_heat_flux")
             import :: c_int, c_double, c_ptr
             real(c_double), intent(in) :: ts(*), ta(*), wind(*), rhoa(*)
             real(c_double), value :: csh, cap
             type(c_ptr), value :: shf
             integer(c_int), value :: n
         end function
-        pure integer(c_int) function semic_lhf_c(ts, wind, shum, sp, rhoatm, mask, clh, eps, cls, clv, lhf, subl, evap, n) &
+        integer(c_int) function semic_lhf_c(ts, wind, shum, sp, rhoatm, mask, clh, eps, cls, clv, lhf, subl, evap, n) &
                 bind(C, name="semic_latent_heat_flux")
             import :: c_int, c_double, c_ptr
             real(c_double), intent(in) :: ts(*), wind(*), shum(*), sp(*), rhoatm(*)
@@ -186,12 +186,26 @@ module surface_physics
             type(c_ptr), value :: lhf, subl, evap
             integer(c_int), value :: n
         end function
-        pure integer(c_int) function semic_lwu_c(ts, sigma, lwout, n) bind(C, name="semic_longwave_upward")
+        integer(c_int) function semic_lwu_c(ts, sigma, lwout, n) bind(C, name="semic_longwave_upward")
             import :: c_int, c_double, c_ptr
             real(c_double), intent(in) :: ts(*)
             real(c_double), value :: sigma
             type(c_ptr), value :: lwout
             integer(c_int), value :: n
+        end function
+        pure real(c_double) function semic_shf_1(ts, ta, wind, rhoa, csh, cap) bind(C, name="semic_sensible_heat_flux_1")
+            import :: c_double
+            real(c_double), value :: ts, ta, wind, rhoa, csh, cap
+        end function
+        pure real(c_double) function semic_lhf_1(ts, wind, shum, sp, rhoatm, mask, clh, eps, cls, clv, which) &
+                bind(C, name="semic_latent_heat_flux_1")
+            import :: c_int, c_double
+            real(c_double), value :: ts, wind, shum, sp, rhoatm, clh, eps, cls, clv
+            integer(c_int), value :: mask, which
+        end function
+        pure real(c_double) function semic_lwu_1(ts, sigma) bind(C, name="semic_longwave_upward_1")
+            import :: c_double
+            real(c_double), value :: ts, sigma
         end function
     end interface
 
@@ -330,10 +344,7 @@ contains
     elemental subroutine sensible_heat_flux_e(ts, ta, wind, rhoa, csh, cap, shf)
         double precision, intent(in) :: ts, ta, wind, rhoa, csh, cap
         double precision, intent(out) :: shf
-        real(c_double), target :: o(1)
-        integer(c_int) :: rc
-        rc = semic_shf_c([ts], [ta], [wind], [rhoa], csh, cap, c_loc(o), 1_c_int)
-        shf = merge(o(1), ieee_value(o(1), ieee_quiet_nan), rc == 0)      ! a pure procedure cannot stop: failure -> NaN
+        shf = semic_shf_1(ts, ta, wind, rhoa, csh, cap)                    ! a pure procedure cannot stop: failure -> NaN
     end subroutine
 
     !> surface_physics.f90:393-430
@@ -349,13 +360,9 @@ contains
         double precision, intent(in)  :: ts, shum, sp, rhoatm, wind, clh, eps, cls, clv
         integer,          intent(in)  :: mask
         double precision, intent(out) :: lhf, evap, subl
-        real(c_double), target :: o1(1), o2(1), o3(1)
-        integer(c_int) :: rc
-        rc = semic_lhf_c([ts], [wind], [shum], [sp], [rhoatm], [int(mask, c_int)], clh, eps, cls, clv, &
-                         c_loc(o1), c_loc(o2), c_loc(o3), 1_c_int)
-        lhf  = merge(o1(1), ieee_value(o1(1), ieee_quiet_nan), rc == 0)
-        subl = merge(o2(1), ieee_value(o2(1), ieee_quiet_nan), rc == 0)
-        evap = merge(o3(1), ieee_value(o3(1), ieee_quiet_nan), rc == 0)
+        lhf  = semic_lhf_1(ts, wind, shum, sp, rhoatm, int(mask, c_int), clh, eps, cls, clv, 0_c_int)
+        subl = semic_lhf_1(ts, wind, shum, sp, rhoatm, int(mask, c_int), clh, eps, cls, clv, 1_c_int)
+        evap = semic_lhf_1(ts, wind, shum, sp, rhoatm, int(mask, c_int), clh, eps, cls, clv, 2_c_int)
     end subroutine
 
     !> surface_physics.f90:434-438
@@ -368,10 +375,7 @@ contains
     elemental subroutine longwave_upward_e(ts, sigma, lwout)
         double precision, intent(in) :: ts, sigma
         double precision, intent(out) :: lwout
-        real(c_double), target :: o(1)
-        integer(c_int) :: rc
-        rc = semic_lwu_c([ts], sigma, c_loc(o), 1_c_int)
-        lwout = merge(o(1), ieee_value(o(1), ieee_quiet_nan), rc == 0)
+        lwout = semic_lwu_1(ts, sigma)
     end subroutine
 
     !> surface_physics.f90:565-597 (device side; ave and now must both be allocated with surface_alloc)

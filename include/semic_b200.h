@@ -111,6 +111,13 @@ int semic_latent_heat_flux(const double *ts, const double *wind, const double *s
                            const double *rhoatm, const int *mask, double clh, double eps, double cls, double clv,
                            double *lhf, double *subl, double *evap, int n);
 int semic_longwave_upward(const double *ts, double sigma, double *lwout, int n);
+/* One value of the same, as a function RESULT (NaN when the call fails): what a Fortran ELEMENTAL specific can forward to through
+ * a PURE bind(C) interface with VALUE dummies -- no result reaches Fortran through a pointer, so an optimising compiler cannot
+ * assume the call left it untouched.  which: 0 = lhf, 1 = subl, 2 = evap (surface_physics.f90:393-430). */
+double semic_sensible_heat_flux_1(double ts, double ta, double wind, double rhoa, double csh, double cap);
+double semic_latent_heat_flux_1(double ts, double wind, double shum, double sp, double rhoatm, int mask,
+                                double clh, double eps, double cls, double clv, int which);
+double semic_longwave_upward_1(double ts, double sigma);
 /* public constants sigm, cap, eps, cls, clv (surface_physics.f90:129) by name; NaN if unknown */
 double semic_constant(const char *name);
 

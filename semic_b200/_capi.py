@@ -78,6 +78,9 @@ PROTOTYPES = {
     "semic_latent_heat_flux": (C.c_int, [_dp, _dp, _dp, _dp, _dp, _ip, C.c_double, C.c_double, C.c_double,
                                          C.c_double, _dp, _dp, _dp, C.c_int]),
     "semic_longwave_upward": (C.c_int, [_dp, C.c_double, _dp, C.c_int]),
+    "semic_sensible_heat_flux_1": (C.c_double, [C.c_double] * 6),
+    "semic_latent_heat_flux_1": (C.c_double, [C.c_double] * 5 + [C.c_int] + [C.c_double] * 4 + [C.c_int]),
+    "semic_longwave_upward_1": (C.c_double, [C.c_double] * 2),
     "semic_constant": (C.c_double, [C.c_char_p]),
     "semic_state_npts": (C.c_int, [_vp]),
     "semic_state_ld": (C.c_int, [_vp]),

@@ -1209,6 +1209,26 @@ extern "C" int semic_longwave_upward(const double *ts, double sigma, double *lwo
     return run_elemental(2, 1, in, nullptr, sc, 1, 1, out, n);
 }
 
+// one value as the function result (for Fortran ELEMENTAL specifics, see the header); NaN when the call fails
+extern "C" double semic_sensible_heat_flux_1(double ts, double ta, double wind, double rhoa, double csh, double cap)
+{
+    double o = 0.0;
+    return semic_sensible_heat_flux(&ts, &ta, &wind, &rhoa, csh, cap, &o, 1) == SEMIC_OK ? o : std::nan("");
+}
+extern "C" double semic_latent_heat_flux_1(double ts, double wind, double shum, double sp, double rhoatm, int mask, double clh,
+                                           double eps, double cls, double clv, int which)
+{
+    double o[3] = {0.0, 0.0, 0.0};
+    if (which < 0 || which > 2) { set_error("latent_heat_flux_1: which must be 0 (lhf), 1 (subl) or 2 (evap)"); return std::nan(""); }
+    return semic_latent_heat_flux(&ts, &wind, &shum, &sp, &rhoatm, &mask, clh, eps, cls, clv, &o[0], &o[1], &o[2], 1) == SEMIC_OK
+               ? o[which] : std::nan("");
+}
+extern "C" double semic_longwave_upward_1(double ts, double sigma)
+{
+    double o = 0.0;
+    return semic_longwave_upward(&ts, sigma, &o, 1) == SEMIC_OK ? o : std::nan("");
+}
+
 // ------------------------------------------------------------------------------------------------
 // NCCL (resolved lazily so that the library loads on machines without libnccl)
 // ------------------------------------------------------------------------------------------------

@@ -607,6 +607,16 @@ def test_elementals_known_answers():
     lhf0, subl0, evap0 = spm.latent_heat_flux(273.15, 6.0, 0.0, 90000., 1.2, 2, 5e-4, spm.eps, spm.cls, spm.clv)
     q = 5e-4 * 6.0 * 1.2 * (611.2 * spm.eps / (611.2 * (spm.eps - 1.0) + 90000.))
     assert subl0[0] == 0.0 and abs(evap0[0] - q) < 1e-15 and abs(lhf0[0] - q * spm.clv) < 1e-9
+    # the one-value forms (what the Fortran shim's ELEMENTAL specifics forward to) return the array forms' bits
+    from semic_b200 import _capi
+    K = _capi.lib()
+    for i in (0, 150, 232, 233, 300):
+        t = float(ts[i])
+        assert K.semic_longwave_upward_1(t, spm.sigm) == lw[i]
+        assert K.semic_sensible_heat_flux_1(t, t + 1.5, 6.0, 1.2, 2e-3, spm.cap) == shf[i]
+        got = [K.semic_latent_heat_flux_1(t, 6.0, 1e-3, 90000., 1.2, 2, 5e-4, spm.eps, spm.cls, spm.clv, w) for w in (0, 1, 2)]
+        assert got == [lhf[i], subl[i], evap[i]]
+    assert np.isnan(K.semic_latent_heat_flux_1(260., 6.0, 1e-3, 90000., 1.2, 2, 5e-4, spm.eps, spm.cls, spm.clv, 3))
 
 
 # ------------------------------------------------------------------------------------------------------------

@@ -168,6 +168,12 @@ def test_compute_entries_fail_loudly_without_a_gpu():
     assert e.value.code == -2 and "CUDA" in str(e.value)
     with pytest.raises(_capi.SemicError):
         sp.longwave_upward(np.array([273.15]), sp.sigm)
+    # the one-value forms behind the Fortran shim's ELEMENTAL specifics return NaN and leave the error text
+    L = _capi.lib()
+    assert np.isnan(L.semic_longwave_upward_1(273.15, sp.sigm))
+    assert np.isnan(L.semic_sensible_heat_flux_1(260.0, 262.0, 6.0, 1.2, 2e-3, sp.cap))
+    assert np.isnan(L.semic_latent_heat_flux_1(260.0, 6.0, 1e-3, 9e4, 1.2, 2, 5e-4, sp.eps, sp.cls, sp.clv, 0))
+    assert b"CUDA" in L.semic_last_error()
 
 
 def test_driver_namelist_and_shards(tmp_path):
