@@ -381,3 +381,65 @@ def test_elemental_procedures_only_reference_pure_interfaces_and_generics_name_r
                 if f != cur and _call_sites(s, f):
                     assert f in pure, "%s (elemental) references %s, which is not pure" % (cur, f)
             assert not re.match(r"(call check|error stop|stop|write|print)\b", low), "%s: %s" % (cur, s)
+
+
+REF = "/root/reference/surface_physics.f90"
+
+
+def _ref_logical_lines():
+    out, cur = [], ""
+    for raw in open(REF):
+        code = raw.split("!")[0].strip()
+        if not code:
+            continue
+        if code.startswith("&"):
+            code = code[1:].lstrip()
+        if code.endswith("&"):
+            cur += code[:-1] + " "
+            continue
+        out.append(cur + code)
+        cur = ""
+    return out
+
+
+@pytest.mark.skipif(not os.path.exists(REF), reason="the reference tree is not on this machine")
+def test_types_and_public_procedures_match_the_reference_module():
+    """drop-in: same type names, same component names (order included), same procedure names and dummy-argument lists as
+    surface_physics.f90 (the reference is read where it lies; nothing is copied)"""
+    ref, shim = _ref_logical_lines(), _logical_lines()
+    for t in ("surface_param_class", "boundary_opt_class", "surface_physics_class"):
+        assert _type_members(shim, t) == _type_members(ref, t), t
+    # surface_state_class: the reference's components, then the shim's handle
+    want = _type_members(ref, "surface_state_class")
+    got = _type_members(shim, "surface_state_class")
+    assert got[:len(want)] == want and got[len(want):] == ["handle"]
+    low_ref, low_shim = "\n".join(ref).lower(), "\n".join(shim).lower()
+    for m in re.finditer(r"^\s*(?:elemental\s+)?subroutine\s+(\w+)\s*\(([^)]*)\)", low_ref, re.M):
+        name, args = m.group(1), [a.strip() for a in m.group(2).split(",")]
+        if name in ("field_average", "diurnal_cycle", "albedo_isba", "albedo_slater", "albedo_denby"):
+            continue                                                    # private helpers of the reference (not in its public list, :121-130)
+        mm = re.search(r"subroutine\s+%s(?:_v)?\s*\(([^)]*)\)" % name, low_shim)
+        assert mm, "%s is missing from the shim" % name
+        assert [a.strip() for a in mm.group(1).split(",")] == args, name
+
+
+def _public_names(lines):
+    names = []
+    for s in lines:
+        m = re.match(r"public\s*::\s*(.*)$", s.lower())
+        if m:
+            names += [n.strip() for n in m.group(1).split(",")]
+    return sorted(names)
+
+
+def test_public_list_is_the_reference_modules():
+    """everything else (helpers, bind(C) twins, field ids, pi/t0/...) is private, so no helper name can clash in a user program"""
+    lines = _logical_lines()
+    assert any(s.lower() == "private" for s in lines)
+    want = sorted("""mass_balance energy_balance surface_energy_and_mass_balance surface_physics_class surface_state_class
+                     surface_param_class boundary_opt_class surface_physics_par_load surface_alloc surface_dealloc
+                     surface_boundary_define surface_physics_average print_param print_boundary_opt sigm cap eps cls clv
+                     longwave_upward latent_heat_flux sensible_heat_flux""".split())
+    assert _public_names(lines) == want
+    if os.path.exists(REF):
+        assert _public_names(_ref_logical_lines()) == want
